@@ -1,0 +1,133 @@
+/*
+ * srggnn.h -- C ABI of libsrggnn.so: the B200 (sm_100a) implementation of the GGNN role-graph stage of
+ * vFones/situation-recognition.  The reference has no FFI layer (its boundary is the Python class API of
+ * model.py), so every entry point below cites the reference code it replaces.  The Python host side
+ * (situation_recognition_b200/) binds these with ctypes; INTEGRATION.md shows the stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers owned by the caller (torch `tensor.data_ptr()`), row-major;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = OK, non-zero = error; srg_last_error() returns a thread-local message;
+ *   - no exceptions cross the ABI; a handle is bound to one device and is not thread-safe;
+ *   - there is NO CPU fallback: on a machine without an sm_100a GPU every compute call fails.
+ */
+#ifndef SRGGNN_H_
+#define SRGGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct srg_handle srg_handle;
+
+enum { SRG_DT_F32 = 1, SRG_DT_BF16 = 2 };
+/* arithmetic of the tensor-core contractions:
+ *   SRG_PREC_BF16 : bf16 operands, fp32 accumulate (training / throughput mode)
+ *   SRG_PREC_FP32 : 3-term bf16 split (hi*hi + hi*lo + lo*hi), fp32 accumulate -- fp32-parity mode, forward only */
+enum { SRG_PREC_BF16 = 0, SRG_PREC_FP32 = 1 };
+/* GGSNN.forward(..., verb=True|False), model.py:59-77 */
+enum { SRG_MODE_NOUN = 0, SRG_MODE_VERB = 1 };
+
+const char* srg_last_error(void);
+int srg_version(void);
+
+/* FCGGNN.__init__ (model.py:90-111): D = hidden size (2048), R = encoder.get_max_role_count() (6), T = 4 (model.py:60),
+ * n_verbs/n_roles/n_labels = encoder.get_num_{verbs,roles,labels}().  `cta_group` = 1 or 2 CTAs per tcgen05.mma. */
+int srg_create(srg_handle** out, int device, int D, int R, int T, int n_verbs, int n_roles, int n_labels);
+int srg_destroy(srg_handle* h);
+int srg_set_cta_group(srg_handle* h, int cta_group);
+
+/* imsitu_encoder.roles_to_verb_tensor_list (imsitu_encoder.py:71-89) and get_role_count (158-159) as flat host tables:
+ * verb2roles[v*R + r] (pad value = n_roles), role_count[v]. */
+int srg_set_tables(srg_handle* h, const int32_t* verb2roles, const int32_t* role_count);
+
+/* imsitu_encoder.get_role_ids_batch (imsitu_encoder.py:172-180) + get_adj_matrix_noself (209-229), bit-exact:
+ * role_idx[b,r] = verb2roles[verb[b], r];  mask[b,i,j] = (i<n && j<n && i!=j) || (i>=n && i==j), n = role_count[verb[b]].
+ * Either output may be NULL.  Returns an error flag in *bad_verb (device int, nullable) if a verb id is out of range. */
+int srg_gather_mask(srg_handle* h, const int64_t* verb, int B, int64_t* role_idx, float* mask, int* bad_verb,
+                    void* stream);
+
+/* The 7 shared GGSNN linears + both classifiers (model.py:47-56,105-111); fp32, nn.Linear layout [out, in]. */
+typedef struct srg_params {
+  const float *W_p, *b_p;
+  const float *W_z, *b_Wz, *U_z, *b_Uz;
+  const float *W_r, *b_Wr, *U_r, *b_Ur;
+  const float *W_h, *b_Wh, *U_h, *b_Uh;
+  const float *Wc_verb, *bc_verb;   /* verb_classifier.1 : [n_verbs, D]  */
+  const float *Wc_noun, *bc_noun;   /* nouns_classifier.1: [n_labels, D] */
+} srg_params;
+
+/* Gradient accumulators (fp32, same shapes as srg_params; kernels ACCUMULATE into them, caller zeroes). */
+typedef struct srg_grads {
+  float *W_p, *b_p;
+  float *W_z, *b_Wz, *U_z, *b_Uz;
+  float *W_r, *b_Wr, *U_r, *b_Ur;
+  float *W_h, *b_Wh, *U_h, *b_Uh;
+  float *Wc_verb, *bc_verb;
+  float *Wc_noun, *bc_noun;
+  float *role_emb;   /* [n_roles+1, D] (padding row never touched) */
+  float *verb_emb;   /* [n_verbs, D] */
+} srg_grads;
+
+/* Convert/pack the fp32 parameters into the bf16 tensor-core operand layout held by the handle.
+ * Must be called after every optimizer step (weights changed) and before the forward calls. */
+int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* stream);
+
+/* Bytes of caller-provided workspace needed by one forward(+backward) pass over `rows` graph nodes
+ * (rows = B*R for SRG_MODE_NOUN, B for SRG_MODE_VERB). */
+size_t srg_workspace_bytes(srg_handle* h, int mode, int B, int precision, int save_for_backward);
+
+/* predict_nouns minus the backbone (model.py:117-155):
+ *   role gather + mask (117,147) -> node = relu(feat * role_emb[role_idx] * verb_emb[verb]) (124-144)
+ *   -> GGSNN(node, mask) (151) -> Dropout + Linear (152) -> logits[B*R, ldl] (first n_labels columns valid).
+ * feat: fp32 [B, D]; verb: int64 [B]; keep: uint8 [B*R, D] dropout keep-mask or NULL (eval / p == 0);
+ * out_role_idx / out_mask are optional copies of the gather results (NULL to skip). */
+int srg_nouns_forward(srg_handle* h, const float* feat, const int64_t* verb, int B, const float* role_emb,
+                      const float* verb_emb, const uint8_t* keep, float drop_p, float* logits, int64_t ldl,
+                      int precision, int save_for_backward, void* workspace, size_t workspace_bytes, void* stream);
+
+/* predict_verb minus the backbone (model.py:160-168): node = relu(feat) -> GGSNN(verb=True) -> Dropout + Linear. */
+int srg_verb_forward(srg_handle* h, const float* feat, int B, const uint8_t* keep, float drop_p, float* logits,
+                     int64_t ldl, int precision, int save_for_backward, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* GGSNN.forward (model.py:59-86) on caller-provided node states: hidden fp32 [rows, D] is updated in place.
+ * mask: fp32 [B, R, R] (SRG_MODE_NOUN, rows = B*R) or NULL (SRG_MODE_VERB, rows = B). */
+int srg_ggnn_forward(srg_handle* h, int mode, float* hidden, const float* mask, int B, int precision,
+                     int save_for_backward, void* workspace, size_t workspace_bytes, void* stream);
+
+/* FCGGNN.nouns_loss (model.py:189-201): sum over the 3 annotations of CrossEntropy(ignore_index = n_labels), each a
+ * mean over its non-ignored targets.  counts: device fp32 [3] = number of non-ignored targets per annotation over the
+ * GLOBAL batch (srg_count_targets, all-reduced by the caller when the batch is sharded).  loss: device fp32 scalar,
+ * accumulated (+=).  dlogits: fp32 [B*R, ldl] or NULL; receives grad_scale * dLoss/dlogits (padding columns = 0). */
+int srg_count_targets(srg_handle* h, const int64_t* gt_nouns, int B, float* counts, void* stream);
+int srg_nouns_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_nouns, int B,
+                   const float* counts, float* loss, float* dlogits, float grad_scale, void* stream);
+
+/* FCGGNN.verb_loss (model.py:182-187): CrossEntropy(pred_verb[B, n_verbs], gt_verb[B]), mean over inv_batch = 1/B_global. */
+int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B, float inv_batch,
+                  float* loss, float* dlogits, float grad_scale, void* stream);
+
+/* autograd backward of srg_nouns_forward / srg_verb_forward (sr.py:76-79).  `workspace` must be the one used by the
+ * matching forward call with save_for_backward = 1.  dlogits: fp32 [rows, ldl].  Gradients accumulate into `g`. */
+int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const float* feat, const int64_t* verb, int B,
+                       const float* role_emb, const float* verb_emb, const uint8_t* keep, float drop_p,
+                       const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream);
+int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int B, const uint8_t* keep, float drop_p,
+                      const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Raw tensor-core GEMM (tests / micro-benchmarks):  C[M,N] = alpha * A[M,K] * B[N,K]^T + bias[N]
+ * a_mn / b_mn = 1: the operand is stored transposed (A as [K,M], B as [K,N]).  c_dtype: SRG_DT_F32 | SRG_DT_BF16.
+ * reduce = 1 (fp32 only): C += ... with k_splits-way split-K. */
+int srg_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* C, int64_t ldc,
+                  int c_dtype, int M, int N, int K, const float* bias, float alpha, int cta_group, int k_splits,
+                  int reduce, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRGGNN_H_ */

@@ -1,0 +1,59 @@
+// C-ABI entry points that expose the raw tcgen05 GEMM (used by the unit tests and the micro-benchmarks).
+#include "host.cuh"
+#include "../../include/srggnn.h"
+
+using namespace srg;
+
+namespace srg {
+int query_device(DeviceInfo* d) {
+  int dev = 0;
+  SRG_CUDA(cudaGetDevice(&dev));
+  if (d->device == dev && d->num_sms > 0) return SRG_OK;
+  cudaDeviceProp prop;
+  SRG_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return set_error(SRG_ERR_UNSUPPORTED, "srggnn needs an sm_100a GPU (found sm_%d%d)", prop.major, prop.minor);
+  d->device = dev;
+  d->num_sms = prop.multiProcessorCount;
+  return SRG_OK;
+}
+}  // namespace srg
+
+extern "C" {
+
+const char* srg_last_error(void) { return g_last_error; }
+
+int srg_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* C, int64_t ldc,
+                  int c_dtype, int M, int N, int K, const float* bias, float alpha, int cg, int k_splits, int reduce,
+                  void* stream) {
+  static thread_local DeviceInfo dev;
+  SRG_TRY(query_device(&dev));
+  GemmProblem p;
+  p.cg = cg;
+  p.a_mn = a_mn != 0;
+  p.b_mn = b_mn != 0;
+  p.M = M;
+  p.N = N;
+  p.nseg = 1;
+  p.seg[0].a = p.a_mn ? mat(A, K, M, lda, DT_BF16) : mat(A, M, K, lda, DT_BF16);
+  p.seg[0].k_off = 0;
+  p.seg[0].k_len = K;
+  p.b = p.b_mn ? mat(B, K, N, ldb, DT_BF16) : mat(B, N, K, ldb, DT_BF16);
+  p.alpha = alpha;
+  p.bias = bias;
+  p.bias_scale = 1.f;
+  p.k_splits = k_splits;
+  if (c_dtype == SRG_DT_F32) {
+    p.epi = EPI_STORE_F32;
+    p.flags = reduce ? FLAG_REDUCE : 0;
+    p.io[0] = mat(C, M, N, ldc, DT_F32);
+  } else if (c_dtype == SRG_DT_BF16) {
+    p.epi = EPI_STORE_BF16;
+    p.io[0] = mat(C, M, N, ldc, DT_BF16);
+  } else {
+    return set_error(SRG_ERR_ARG, "srg_gemm_bf16: bad c_dtype %d", c_dtype);
+  }
+  return run_gemm(p, dev, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// Host-side plumbing shared by the C-ABI entry points: error reporting, TMA descriptor encoding,
+// and the GEMM launcher that maps a problem description onto one gemm_kernel instantiation.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "gemm.cuh"
+
+namespace srg {
+
+// ---------------------------------------------------------------- errors (no exceptions cross the ABI)
+inline thread_local char g_last_error[512] = "";
+
+inline int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+enum : int {
+  SRG_OK = 0,
+  SRG_ERR_ARG = 1,
+  SRG_ERR_CUDA = 2,
+  SRG_ERR_UNSUPPORTED = 3,
+  SRG_ERR_WORKSPACE = 4,
+};
+
+#define SRG_CUDA(expr)                                                                                 \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return ::srg::set_error(::srg::SRG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                                     \
+  } while (0)
+
+#define SRG_CHECK(cond, ...)                                              \
+  do {                                                                    \
+    if (!(cond)) return ::srg::set_error(::srg::SRG_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define SRG_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+// ---------------------------------------------------------------- TMA descriptors
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+enum DType : int { DT_NONE = 0, DT_F32 = 1, DT_BF16 = 2 };
+
+// Row-major 2-D tensor [rows, cols] with leading dimension `ld` (elements); box = [box_rows, box_cols];
+// SWIZZLE_128B (box_cols * elem_size must be 128 bytes).
+inline int make_tmap(CUtensorMap* out, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld,
+                     int box_rows, int box_cols) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error(SRG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int es = (dtype == DT_F32) ? 4 : 2;
+  SRG_CHECK(box_cols * es == 128, "TMA box must span 128 bytes (got %d)", box_cols * es);
+  SRG_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  SRG_CHECK(((ld * es) & 15) == 0, "TMA row pitch must be a multiple of 16 bytes (ld=%lld)", (long long)ld);
+  SRG_CHECK(rows > 0 && cols > 0, "empty tensor for TMA (%lld x %lld)", (long long)rows, (long long)cols);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, dtype == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(SRG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r,
+                     (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
+  return SRG_OK;
+}
+
+// ---------------------------------------------------------------- GEMM problem description
+struct Mat {
+  const void* ptr = nullptr;
+  int64_t rows = 0, cols = 0, ld = 0;  // row-major storage
+  int dtype = DT_NONE;
+};
+inline Mat mat(const void* p, int64_t rows, int64_t cols, int64_t ld, int dtype) {
+  Mat m;
+  m.ptr = p; m.rows = rows; m.cols = cols; m.ld = ld; m.dtype = dtype;
+  return m;
+}
+
+struct GemmSeg {
+  Mat a;        // K-major: [M, >=k_off+K_s] ; MN-major: [>=k_off+K_s, M]
+  int k_off;    // start along K inside `a`
+  int k_len;    // multiple of 64
+};
+
+struct GemmProblem {
+  int cg = 2;           // CTAs per UMMA (1 or 2)
+  bool a_mn = false, b_mn = false;
+  int epi = EPI_STORE_F32;
+  bool f32 = false;     // fp32-parity arithmetic in the epilogue
+  int M = 0, N = 0;     // N multiple of the column tile
+  int nseg = 0;
+  GemmSeg seg[kMaxSeg];
+  Mat b;                // K-major: [N, Ktot]; MN-major: [Ktot, N]
+  Mat io[kMaxIoMaps];
+  float alpha = 1.f;
+  const float* bias = nullptr;
+  float bias_scale = 1.f;
+  int n_split = 0, n_valid = 0;
+  float* stats = nullptr;
+  int flags = 0;
+  int k_splits = 1;
+  int max_clusters = 0;  // 0 = all SMs
+};
+
+struct DeviceInfo {
+  int device = -1;
+  int num_sms = 0;
+};
+
+template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool F32>
+inline int launch_gemm_inst(const GemmProblem& p, const GemmMaps& maps, const GemmArgs& args, const DeviceInfo& dev,
+                            cudaStream_t stream) {
+  using Cfg = GemmCfg<CG, BLOCK_N, EPI, F32>;
+  auto kern = gemm_kernel<CG, BLOCK_N, A_MN, B_MN, EPI, F32>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int num_m_tiles = (p.M + kTileM * CG - 1) / (kTileM * CG);
+  const int total_work = num_m_tiles * (p.N / BLOCK_N) * p.k_splits;
+  int clusters = dev.num_sms / CG;
+  if (p.max_clusters > 0 && p.max_clusters < clusters) clusters = p.max_clusters;
+  if (total_work < clusters) clusters = total_work;
+  if (clusters <= 0) return SRG_OK;
+
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * CG, 1, 1);
+  cfg.blockDim = dim3(kNumThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CG > 1) ? 1 : 0;
+  SRG_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, args));
+  return SRG_OK;
+}
+
+template <int CG>
+inline int tile_n() { return CG == 2 ? 256 : 128; }
+
+template <int CG, int BLOCK_N>
+inline int dispatch_gemm(const GemmProblem& p, const GemmMaps& maps, const GemmArgs& args, const DeviceInfo& dev,
+                         cudaStream_t stream) {
+#define SRG_CASE(AMN, BMN, E, F)                                                                     \
+  if (p.a_mn == AMN && p.b_mn == BMN && p.epi == E && p.f32 == F)                                    \
+    return launch_gemm_inst<CG, BLOCK_N, AMN, BMN, E, F>(p, maps, args, dev, stream);
+  SRG_CASE(false, false, EPI_STORE_BF16, false)
+  SRG_CASE(false, false, EPI_STORE_F32, false)
+  SRG_CASE(false, false, EPI_ZR, false)
+  SRG_CASE(false, false, EPI_ZR, true)
+  SRG_CASE(false, false, EPI_H, false)
+  SRG_CASE(false, false, EPI_H, true)
+  SRG_CASE(false, false, EPI_LOGITS, false)
+  SRG_CASE(false, true, EPI_STORE_BF16, false)
+  SRG_CASE(false, true, EPI_STORE_F32, false)
+  SRG_CASE(false, true, EPI_DRH, false)
+  SRG_CASE(true, true, EPI_STORE_F32, false)
+#undef SRG_CASE
+  return set_error(SRG_ERR_UNSUPPORTED, "no gemm kernel for a_mn=%d b_mn=%d epi=%d f32=%d", (int)p.a_mn, (int)p.b_mn,
+                   p.epi, (int)p.f32);
+}
+
+inline int io_box_cols(int dtype) { return dtype == DT_F32 ? 32 : 64; }
+
+// Encode descriptors and launch.
+inline int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t stream) {
+  SRG_CHECK(p.cg == 1 || p.cg == 2, "cg must be 1 or 2");
+  const int block_n = (p.cg == 2) ? 256 : 128;
+  SRG_CHECK(p.M > 0, "gemm: M must be positive");
+  SRG_CHECK(p.N > 0 && p.N % block_n == 0, "gemm: N=%d must be a positive multiple of %d", p.N, block_n);
+  SRG_CHECK(p.nseg >= 1 && p.nseg <= kMaxSeg, "gemm: bad segment count %d", p.nseg);
+  SRG_CHECK(p.k_splits >= 1, "gemm: k_splits must be >= 1");
+  SRG_CHECK(p.k_splits == 1 || (p.epi == EPI_STORE_F32 && (p.flags & FLAG_REDUCE)),
+            "gemm: split-K needs the fp32 reduce epilogue");
+
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  GemmArgs args;
+  memset(&args, 0, sizeof(args));
+  args.M = p.M;
+  args.N = p.N;
+  args.nseg = p.nseg;
+
+  // A segments: distinct matrices share a descriptor slot
+  const void* aptr[kMaxAMaps];
+  int n_amaps = 0;
+  int ktot = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    const GemmSeg& sg = p.seg[s];
+    SRG_CHECK(sg.k_len > 0 && sg.k_len % kBlockK == 0, "gemm: segment %d K=%d not a multiple of 64", s, sg.k_len);
+    SRG_CHECK(sg.a.dtype == DT_BF16, "gemm: A must be bf16");
+    int mi = -1;
+    for (int j = 0; j < n_amaps; ++j)
+      if (aptr[j] == sg.a.ptr) mi = j;
+    if (mi < 0) {
+      SRG_CHECK(n_amaps < kMaxAMaps, "gemm: more than %d distinct A matrices", kMaxAMaps);
+      mi = n_amaps++;
+      aptr[mi] = sg.a.ptr;
+      if (!p.a_mn) {
+        SRG_CHECK(sg.a.rows >= p.M, "gemm: A segment %d has %lld rows < M=%d", s, (long long)sg.a.rows, p.M);
+        SRG_TRY(make_tmap(&maps.a[mi], sg.a.ptr, DT_BF16, p.M, sg.a.cols, sg.a.ld, kTileM, kBlockK));
+      } else {
+        SRG_CHECK(sg.a.cols >= p.M, "gemm: MN-major A segment %d has %lld cols < M=%d", s, (long long)sg.a.cols, p.M);
+        SRG_TRY(make_tmap(&maps.a[mi], sg.a.ptr, DT_BF16, sg.a.rows, p.M, sg.a.ld, kBlockK, 64));
+      }
+    }
+    const int64_t kext = p.a_mn ? sg.a.rows : sg.a.cols;
+    SRG_CHECK(sg.k_off >= 0 && sg.k_off + sg.k_len <= kext, "gemm: segment %d K range [%d,%d) outside A (%lld)", s,
+              sg.k_off, sg.k_off + sg.k_len, (long long)kext);
+    args.seg_map[s] = mi;
+    args.seg_acol[s] = sg.k_off;
+    args.seg_kb[s] = sg.k_len / kBlockK;
+    ktot += sg.k_len;
+  }
+  for (int j = n_amaps; j < kMaxAMaps; ++j) maps.a[j] = maps.a[0];
+  args.total_kb = ktot / kBlockK;
+  SRG_CHECK(p.k_splits <= args.total_kb, "gemm: k_splits %d > k-blocks %d", p.k_splits, args.total_kb);
+
+  SRG_CHECK(p.b.dtype == DT_BF16, "gemm: B must be bf16");
+  if (!p.b_mn) {
+    SRG_CHECK(p.b.rows >= p.N && p.b.cols >= ktot, "gemm: B [%lld,%lld] smaller than [N=%d,K=%d]",
+              (long long)p.b.rows, (long long)p.b.cols, p.N, ktot);
+    SRG_TRY(make_tmap(&maps.b, p.b.ptr, DT_BF16, p.N, ktot, p.b.ld, block_n / p.cg, kBlockK));
+  } else {
+    SRG_CHECK(p.b.rows >= ktot && p.b.cols >= p.N, "gemm: MN-major B [%lld,%lld] smaller than [K=%d,N=%d]",
+              (long long)p.b.rows, (long long)p.b.cols, ktot, p.N);
+    SRG_TRY(make_tmap(&maps.b, p.b.ptr, DT_BF16, ktot, p.N, p.b.ld, kBlockK, 64));
+  }
+  bool have_io0 = false;
+  for (int i = 0; i < kMaxIoMaps; ++i) {
+    if (p.io[i].dtype == DT_NONE || p.io[i].ptr == nullptr) continue;
+    SRG_TRY(make_tmap(&maps.io[i], p.io[i].ptr, p.io[i].dtype, p.io[i].rows, p.io[i].cols, p.io[i].ld, 32,
+                      io_box_cols(p.io[i].dtype)));
+    if (i == 0) have_io0 = true;
+  }
+  (void)have_io0;
+
+  args.k_splits = p.k_splits;
+  args.alpha = p.alpha;
+  args.bias = p.bias;
+  args.bias_scale = p.bias_scale;
+  args.n_split = p.n_split;
+  args.n_valid = p.n_valid;
+  args.stats = p.stats;
+  args.flags = p.flags;
+
+  if (p.cg == 2) return dispatch_gemm<2, 256>(p, maps, args, dev, stream);
+  return dispatch_gemm<1, 128>(p, maps, args, dev, stream);
+}
+
+}  // namespace srg
