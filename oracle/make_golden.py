@@ -66,9 +66,9 @@ def run_model_case(ref_model, enc, D, B, seed, train_json):
     for p in model.parameters():
         p.requires_grad_(True)
     pred_verb, pred_nouns, gt_pred_nouns = model(feat, gt_verb)
-    vl = model.verb_loss(pred_verb, gt_verb) if False else torch.nn.CrossEntropyLoss()(pred_verb, gt_verb)
-    # model.verb_loss / nouns_loss call .cuda() on the loss module (model.py:184,191), which needs a GPU build;
+    # model.verb_loss / nouns_loss call .cuda() on the loss module (model.py:184,191), which needs a GPU;
     # the loss arithmetic itself is reproduced with the same torch calls (model.py:185,195-199).
+    vl = torch.nn.CrossEntropyLoss()(pred_verb, gt_verb)
     nl_fn = torch.nn.CrossEntropyLoss(ignore_index=L)
     pn_t = pred_nouns.transpose(1, 2)
     gpn_t = gt_pred_nouns.transpose(1, 2)
@@ -110,6 +110,7 @@ def main():
     enc_items = [enc_over.encode(over[k]) for k in over]
     tabs["encode_verbs"] = np.array([v for v, _ in enc_items], dtype=np.int64)
     tabs["encode_labels"] = torch.stack([l for _, l in enc_items]).numpy()
+    tabs["annotations_json"] = np.array(json.dumps(over))   # the encoder's input, so the fixture is self-contained
     np.savez_compressed(os.path.join(OUT, "encoder_overfitting.npz"), **tabs)
 
     # (2) synthetic imSitu-shaped vocabulary: 504 / 190 / 2001 / 6
