@@ -1,0 +1,66 @@
+// HBM-bound kernels of the GGNN role-graph stage: index gather / mask build, node initialisation, neighbour
+// aggregation, weight packing, dropout, cross-entropy, and the elementwise pieces of the backward pass.
+// All of them are launched on grids sized in multiples of the SM count with 16-byte vector accesses.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+namespace srg {
+
+typedef __nv_bfloat16 bf16;
+
+int launch_gather_mask(const int32_t* verb2roles, const int32_t* role_count, int n_verbs, int R, const int64_t* verb,
+                       int B, int64_t* role_idx, float* mask, int* bad, cudaStream_t s);
+
+// node[b*R+r, :] = relu(feat[b,:] * role_emb[verb2roles[verb[b], r], :] * verb_emb[verb[b], :])   (model.py:124-144)
+int launch_node_init_noun(const float* feat, const float* role_emb, const float* verb_emb, const int64_t* verb,
+                          const int32_t* verb2roles, int n_verbs, int B, int R, int D, float* h32, bf16* hb_hi,
+                          bf16* hb_lo, cudaStream_t s);
+// node = relu(feat)  (model.py:160)
+int launch_node_init_verb(const float* feat, int B, int D, float* h32, bf16* hb_hi, bf16* hb_lo, cudaStream_t s);
+// fp32 -> bf16 hi (+lo)
+int launch_split_cast(const float* x, int64_t n, bf16* hi, bf16* lo, cudaStream_t s);
+
+// a[b,i,:] = sum_j mask[b,i,j] * h[b,j,:]    (model.py:67-75 with the projection hoisted out of the sum)
+int launch_aggregate(const float* h32, const float* mask, int B, int R, int D, bf16* a_hi, bf16* a_lo,
+                     cudaStream_t s);
+// dh[b,j,:] = dh_acc[b,j,:] + sum_i mask[b,i,j] * da[b,i,:]
+int launch_aggregate_bwd(const float* dh_acc, const float* da, const float* mask, int B, int R, int D, float* dh,
+                         cudaStream_t s);
+
+// dst[r, col_off + c] = hi/lo bf16 part of src[r, c] (r < rows), 0 for rows <= r < rows_pad
+int launch_pack_weight(const float* src, int rows, int cols, int rows_pad, bf16* dst, int64_t ld_dst, int64_t col_off,
+                       int want_lo, cudaStream_t s);
+// dst[i] = a[i] (+ b[i]) for i < n, 0 for n <= i < n_pad
+int launch_pack_bias(const float* a, const float* b, int n, int n_pad, float* dst, cudaStream_t s);
+
+// x = h * keep / (1-p)  -> bf16 hi (+lo)
+int launch_dropout_cast(const float* h32, const uint8_t* keep, float scale, int64_t n, bf16* hi, bf16* lo,
+                        cudaStream_t s);
+// dh = dx * keep / (1-p)   (keep may be null)
+int launch_dropout_bwd(const float* dx, const uint8_t* keep, float scale, int64_t n, float* dh, cudaStream_t s);
+
+int launch_count_targets(const int64_t* gt, int B, int R, int ignore_index, float* counts, cudaStream_t s);
+// one warp per logits row
+int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_t* gt, int B, int R,
+                    const float* counts, float* loss, float* dlogits, float grad_scale, cudaStream_t s);
+int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t* gt, int B, float inv_batch,
+                   float* loss, float* dlogits, float grad_scale, cudaStream_t s);
+// fp32 [rows, ld] (first n_valid columns) -> bf16 [rows, n_pad], zero padded
+int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, cudaStream_t s);
+
+// GRU backward prologue:  dpre_z = dh'*(hc-h)*z*(1-z), dpre_h = dh'*z*(1-hc^2), dh_acc = dh'*(1-z)
+int launch_gru_bwd_pre(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int64_t n, bf16* dpre_z,
+                       bf16* dpre_h, float* dh_acc, cudaStream_t s);
+// out1[c] (+= scale1 * colsum) , out2[c] (+= scale2 * colsum); X bf16 [rows, ld], first n_cols columns
+int launch_colsum(const bf16* X, int64_t ld, int rows, int n_cols, float* out1, float scale1, float* out2,
+                  float scale2, cudaStream_t s);
+// node-init backward (embedding gradients), model.py:132-144
+int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, const float* role_emb,
+                         const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_roles, int B,
+                         int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s);
+
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s);
+
+}  // namespace srg

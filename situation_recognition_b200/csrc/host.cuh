@@ -144,7 +144,7 @@ inline int launch_gemm_inst(const GemmProblem& p, const GemmMaps& maps, const Ge
     attr_done = true;
   }
   const int num_m_tiles = (p.M + kTileM * CG - 1) / (kTileM * CG);
-  const int total_work = num_m_tiles * (p.N / BLOCK_N) * p.k_splits;
+  const int total_work = num_m_tiles * (p.N / BLOCK_N) * args.k_splits;
   int clusters = dev.num_sms / CG;
   if (p.max_clusters > 0 && p.max_clusters < clusters) clusters = p.max_clusters;
   if (total_work < clusters) clusters = total_work;
@@ -219,7 +219,9 @@ inline int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t st
   int ktot = 0;
   for (int s = 0; s < p.nseg; ++s) {
     const GemmSeg& sg = p.seg[s];
-    SRG_CHECK(sg.k_len > 0 && sg.k_len % kBlockK == 0, "gemm: segment %d K=%d not a multiple of 64", s, sg.k_len);
+    // a K tail (< 64) is legal only in the last segment: TMA zero-fills beyond the tensor extent of A and B
+    SRG_CHECK(sg.k_len > 0 && (sg.k_len % kBlockK == 0 || s == p.nseg - 1), "gemm: segment %d K=%d not a multiple of 64",
+              s, sg.k_len);
     SRG_CHECK(sg.a.dtype == DT_BF16, "gemm: A must be bf16");
     int mi = -1;
     for (int j = 0; j < n_amaps; ++j)
@@ -241,21 +243,30 @@ inline int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t st
               sg.k_off, sg.k_off + sg.k_len, (long long)kext);
     args.seg_map[s] = mi;
     args.seg_acol[s] = sg.k_off;
-    args.seg_kb[s] = sg.k_len / kBlockK;
+    args.seg_kb[s] = (sg.k_len + kBlockK - 1) / kBlockK;
     ktot += sg.k_len;
+    if (sg.k_len % kBlockK != 0)
+      SRG_CHECK(sg.k_off + sg.k_len == kext, "gemm: a K tail must end at the tensor extent (zero fill)");
   }
   for (int j = n_amaps; j < kMaxAMaps; ++j) maps.a[j] = maps.a[0];
-  args.total_kb = ktot / kBlockK;
-  SRG_CHECK(p.k_splits <= args.total_kb, "gemm: k_splits %d > k-blocks %d", p.k_splits, args.total_kb);
+  args.total_kb = (ktot + kBlockK - 1) / kBlockK;
+  // every split must own at least one k-block (an empty split would never signal its accumulator)
+  int k_splits = p.k_splits < args.total_kb ? p.k_splits : args.total_kb;
+  {
+    const int per = (args.total_kb + k_splits - 1) / k_splits;
+    k_splits = (args.total_kb + per - 1) / per;
+  }
 
   SRG_CHECK(p.b.dtype == DT_BF16, "gemm: B must be bf16");
   if (!p.b_mn) {
     SRG_CHECK(p.b.rows >= p.N && p.b.cols >= ktot, "gemm: B [%lld,%lld] smaller than [N=%d,K=%d]",
               (long long)p.b.rows, (long long)p.b.cols, p.N, ktot);
+    SRG_CHECK(ktot % kBlockK == 0 || p.b.cols == ktot, "gemm: K tail needs B cols == K");
     SRG_TRY(make_tmap(&maps.b, p.b.ptr, DT_BF16, p.N, ktot, p.b.ld, block_n / p.cg, kBlockK));
   } else {
     SRG_CHECK(p.b.rows >= ktot && p.b.cols >= p.N, "gemm: MN-major B [%lld,%lld] smaller than [K=%d,N=%d]",
               (long long)p.b.rows, (long long)p.b.cols, ktot, p.N);
+    SRG_CHECK(ktot % kBlockK == 0 || p.b.rows == ktot, "gemm: K tail needs B rows == K");
     SRG_TRY(make_tmap(&maps.b, p.b.ptr, DT_BF16, ktot, p.N, p.b.ld, kBlockK, 64));
   }
   bool have_io0 = false;
@@ -267,7 +278,7 @@ inline int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t st
   }
   (void)have_io0;
 
-  args.k_splits = p.k_splits;
+  args.k_splits = k_splits;
   args.alpha = p.alpha;
   args.bias = p.bias;
   args.bias_scale = p.bias_scale;

@@ -1,0 +1,627 @@
+// HBM-bound kernels of the GGNN role-graph stage (see elementwise.cuh).
+#include "elementwise.cuh"
+#include "host.cuh"
+
+namespace srg {
+
+namespace {
+
+constexpr int kMaxR = 8;
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t work, int threads = kThreads, int max_blocks = 148 * 16) {
+  int64_t b = (work + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&lo);
+  r.y = *reinterpret_cast<uint32_t*>(&hi);
+  return r;
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// store 4 values as bf16 hi (and the residual as bf16 lo when lo != nullptr)
+__device__ __forceinline__ void store4_split(bf16* hi, bf16* lo, int64_t idx, float4 v) {
+  *reinterpret_cast<uint2*>(hi + idx) = pack4_bf16(v.x, v.y, v.z, v.w);
+  if (lo != nullptr) {
+    *reinterpret_cast<uint2*>(lo + idx) =
+        pack4_bf16(v.x - bf16_round(v.x), v.y - bf16_round(v.y), v.z - bf16_round(v.z), v.w - bf16_round(v.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+__global__ void k_gather_mask(const int32_t* __restrict__ verb2roles, const int32_t* __restrict__ role_count,
+                              int n_verbs, int R, const int64_t* __restrict__ verb, int B,
+                              int64_t* __restrict__ role_idx, float* __restrict__ mask, int* __restrict__ bad) {
+  const int64_t total = static_cast<int64_t>(B) * R * R;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(t / (R * R));
+    const int ij = static_cast<int>(t % (R * R));
+    const int i = ij / R, j = ij % R;
+    int64_t v = verb[b];
+    const bool ok = (v >= 0 && v < n_verbs);
+    if (!ok) {
+      if (bad != nullptr) *bad = 1;
+      v = 0;
+    }
+    const int n = role_count[v];
+    if (mask != nullptr) {
+      const bool on = (i < n && j < n && i != j) || (i >= n && i == j);
+      mask[t] = on ? 1.0f : 0.0f;
+    }
+    if (role_idx != nullptr && i == 0) role_idx[static_cast<int64_t>(b) * R + j] = verb2roles[v * R + j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ node init
+__global__ void k_node_init_noun(const float* __restrict__ feat, const float* __restrict__ role_emb,
+                                 const float* __restrict__ verb_emb, const int64_t* __restrict__ verb,
+                                 const int32_t* __restrict__ verb2roles, int n_verbs, int B, int R, int D,
+                                 float* __restrict__ h32, bf16* __restrict__ hb_hi, bf16* __restrict__ hb_lo) {
+  const int D4 = D / 4;
+  const int64_t total = static_cast<int64_t>(B) * D4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(t / D4);
+    const int d = static_cast<int>(t % D4) * 4;
+    int64_t v = verb[b];
+    if (v < 0 || v >= n_verbs) v = 0;
+    const float4 f = *reinterpret_cast<const float4*>(feat + static_cast<int64_t>(b) * D + d);
+    const float4 ve = *reinterpret_cast<const float4*>(verb_emb + v * D + d);
+    for (int r = 0; r < R; ++r) {
+      const int idx = verb2roles[v * R + r];
+      const float4 re = *reinterpret_cast<const float4*>(role_emb + static_cast<int64_t>(idx) * D + d);
+      float4 o;
+      // same association as the reference: (img_features * role_embd) * verb_embed_expand
+      o.x = fmaxf((f.x * re.x) * ve.x, 0.f);
+      o.y = fmaxf((f.y * re.y) * ve.y, 0.f);
+      o.z = fmaxf((f.z * re.z) * ve.z, 0.f);
+      o.w = fmaxf((f.w * re.w) * ve.w, 0.f);
+      const int64_t off = (static_cast<int64_t>(b) * R + r) * D + d;
+      *reinterpret_cast<float4*>(h32 + off) = o;
+      store4_split(hb_hi, hb_lo, off, o);
+    }
+  }
+}
+
+__global__ void k_node_init_verb(const float* __restrict__ feat, int64_t n4, float* __restrict__ h32,
+                                 bf16* __restrict__ hb_hi, bf16* __restrict__ hb_lo) {
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 f = *reinterpret_cast<const float4*>(feat + t * 4);
+    f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
+    *reinterpret_cast<float4*>(h32 + t * 4) = f;
+    store4_split(hb_hi, hb_lo, t * 4, f);
+  }
+}
+
+__global__ void k_split_cast(const float* __restrict__ x, int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 f = *reinterpret_cast<const float4*>(x + t * 4);
+    store4_split(hi, lo, t * 4, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ aggregation
+__global__ void k_aggregate(const float* __restrict__ h32, const float* __restrict__ mask, int B, int R, int D,
+                            bf16* __restrict__ a_hi, bf16* __restrict__ a_lo) {
+  const int D4 = D / 4;
+  const int64_t total = static_cast<int64_t>(B) * D4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(t / D4);
+    const int d = static_cast<int>(t % D4) * 4;
+    float4 h[kMaxR];
+#pragma unroll
+    for (int j = 0; j < kMaxR; ++j)
+      if (j < R) h[j] = *reinterpret_cast<const float4*>(h32 + (static_cast<int64_t>(b) * R + j) * D + d);
+    const float* mb = mask + static_cast<int64_t>(b) * R * R;
+#pragma unroll
+    for (int i = 0; i < kMaxR; ++i) {
+      if (i < R) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kMaxR; ++j) {
+          if (j < R) {
+            const float m = __ldg(mb + i * R + j);
+            a.x = fmaf(m, h[j].x, a.x); a.y = fmaf(m, h[j].y, a.y);
+            a.z = fmaf(m, h[j].z, a.z); a.w = fmaf(m, h[j].w, a.w);
+          }
+        }
+        store4_split(a_hi, a_lo, (static_cast<int64_t>(b) * R + i) * D + d, a);
+      }
+    }
+  }
+}
+
+__global__ void k_aggregate_bwd(const float* __restrict__ dh_acc, const float* __restrict__ da,
+                                const float* __restrict__ mask, int B, int R, int D, float* __restrict__ dh) {
+  const int D4 = D / 4;
+  const int64_t total = static_cast<int64_t>(B) * D4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(t / D4);
+    const int d = static_cast<int>(t % D4) * 4;
+    float4 g[kMaxR];
+#pragma unroll
+    for (int i = 0; i < kMaxR; ++i)
+      if (i < R) g[i] = *reinterpret_cast<const float4*>(da + (static_cast<int64_t>(b) * R + i) * D + d);
+    const float* mb = mask + static_cast<int64_t>(b) * R * R;
+#pragma unroll
+    for (int j = 0; j < kMaxR; ++j) {
+      if (j < R) {
+        const int64_t off = (static_cast<int64_t>(b) * R + j) * D + d;
+        float4 a = *reinterpret_cast<const float4*>(dh_acc + off);
+#pragma unroll
+        for (int i = 0; i < kMaxR; ++i) {
+          if (i < R) {
+            const float m = __ldg(mb + i * R + j);
+            a.x = fmaf(m, g[i].x, a.x); a.y = fmaf(m, g[i].y, a.y);
+            a.z = fmaf(m, g[i].z, a.z); a.w = fmaf(m, g[i].w, a.w);
+          }
+        }
+        *reinterpret_cast<float4*>(dh + off) = a;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+__global__ void k_pack_weight(const float* __restrict__ src, int rows, int cols, int rows_pad, bf16* __restrict__ dst,
+                              int64_t ld_dst, int64_t col_off, int want_lo) {
+  const int c2 = cols / 2;
+  const int64_t total = static_cast<int64_t>(rows_pad) * c2;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(t / c2);
+    const int c = static_cast<int>(t % c2) * 2;
+    float2 v = make_float2(0.f, 0.f);
+    if (r < rows) v = *reinterpret_cast<const float2*>(src + static_cast<int64_t>(r) * cols + c);
+    if (want_lo) {
+      v.x -= bf16_round(v.x);
+      v.y -= bf16_round(v.y);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<int64_t>(r) * ld_dst + col_off + c) =
+        __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+
+__global__ void k_pack_bias(const float* __restrict__ a, const float* __restrict__ b, int n, int n_pad,
+                            float* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < n) v = a[i] + (b != nullptr ? b[i] : 0.f);
+    dst[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dropout
+__global__ void k_dropout_cast(const float* __restrict__ h32, const uint8_t* __restrict__ keep, float scale,
+                               int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 f = *reinterpret_cast<const float4*>(h32 + t * 4);
+    const uchar4 k = *reinterpret_cast<const uchar4*>(keep + t * 4);
+    f.x = k.x ? f.x * scale : 0.f;
+    f.y = k.y ? f.y * scale : 0.f;
+    f.z = k.z ? f.z * scale : 0.f;
+    f.w = k.w ? f.w * scale : 0.f;
+    store4_split(hi, lo, t * 4, f);
+  }
+}
+
+__global__ void k_dropout_bwd(const float* __restrict__ dx, const uint8_t* __restrict__ keep, float scale, int64_t n4,
+                              float* __restrict__ dh) {
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 f = *reinterpret_cast<const float4*>(dx + t * 4);
+    if (keep != nullptr) {
+      const uchar4 k = *reinterpret_cast<const uchar4*>(keep + t * 4);
+      f.x = k.x ? f.x * scale : 0.f;
+      f.y = k.y ? f.y * scale : 0.f;
+      f.z = k.z ? f.z * scale : 0.f;
+      f.w = k.w ? f.w * scale : 0.f;
+    }
+    *reinterpret_cast<float4*>(dh + t * 4) = f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cross-entropy
+__global__ void k_count_targets(const int64_t* __restrict__ gt, int B, int R, int ignore_index,
+                                float* __restrict__ counts) {
+  __shared__ int sc[3];
+  if (threadIdx.x < 3) sc[threadIdx.x] = 0;
+  __syncthreads();
+  int local[3] = {0, 0, 0};
+  const int64_t total = static_cast<int64_t>(B) * 3 * R;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int a = static_cast<int>((t / R) % 3);
+    if (gt[t] != ignore_index) local[a]++;
+  }
+  for (int a = 0; a < 3; ++a)
+    if (local[a]) atomicAdd(&sc[a], local[a]);
+  __syncthreads();
+  if (threadIdx.x < 3 && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], static_cast<float>(sc[threadIdx.x]));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per row.  NT = number of targets per row (3 for nouns, 1 for verbs).
+//   loss += sum_a w_a * (lse - logit[t_a]);   dlogits[c] = gs * (sum_a w_a * (p_c - [c == t_a]))
+template <int NT>
+__global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, int n_classes, int rows,
+                                const int64_t* __restrict__ gt, int R, int ignore_index,
+                                const float* __restrict__ counts, float inv_fixed, float* __restrict__ loss,
+                                float* __restrict__ dlogits, float grad_scale) {
+  __shared__ float s_loss[kThreads / 32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  float my_loss = 0.f;
+  for (int row = blockIdx.x * warps_per_block + wib; row < rows; row += gridDim.x * warps_per_block) {
+    const float* lr = logits + static_cast<int64_t>(row) * ldl;
+    int64_t tgt[NT];
+    float w[NT];
+    float wsum = 0.f;
+#pragma unroll
+    for (int a = 0; a < NT; ++a) {
+      if (NT == 3) {
+        const int b = row / R, r = row % R;
+        tgt[a] = gt[(static_cast<int64_t>(b) * 3 + a) * R + r];
+        w[a] = (tgt[a] != ignore_index) ? 1.0f / counts[a] : 0.f;
+      } else {
+        tgt[a] = gt[row];
+        w[a] = inv_fixed;
+      }
+      wsum += w[a];
+    }
+    if (wsum == 0.f && dlogits == nullptr) continue;  // fully ignored row contributes nothing
+    float mx = -INFINITY;
+    for (int c = lane; c < n_classes; c += 32) mx = fmaxf(mx, lr[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < n_classes; c += 32) se += __expf(lr[c] - mx);
+    se = warp_sum(se);
+    const float lse = mx + __logf(se);
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < NT; ++a)
+        if (w[a] != 0.f) my_loss += w[a] * (lse - lr[tgt[a]]);
+    }
+    if (dlogits != nullptr) {
+      float* dr = dlogits + static_cast<int64_t>(row) * ldl;
+      const float inv_se = 1.0f / se;
+      for (int c = lane; c < ldl; c += 32) {
+        float g = 0.f;
+        if (c < n_classes && wsum != 0.f) {
+          g = wsum * __expf(lr[c] - mx) * inv_se;
+#pragma unroll
+          for (int a = 0; a < NT; ++a)
+            if (w[a] != 0.f && tgt[a] == c) g -= w[a];
+          g *= grad_scale;
+        }
+        dr[c] = g;
+      }
+    }
+  }
+  if (lane == 0) s_loss[wib] = my_loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < warps_per_block; ++i) t += s_loss[i];
+    if (t != 0.f) atomicAdd(loss, t);
+  }
+}
+
+__global__ void k_cast_pad(const float* __restrict__ src, int64_t ld, int rows, int n_valid, int n_pad,
+                           bf16* __restrict__ dst) {
+  const int c2 = n_pad / 2;
+  const int64_t total = static_cast<int64_t>(rows) * c2;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(t / c2);
+    const int c = static_cast<int>(t % c2) * 2;
+    const float* s = src + static_cast<int64_t>(r) * ld;
+    const float a = (c < n_valid) ? s[c] : 0.f;
+    const float b = (c + 1 < n_valid) ? s[c + 1] : 0.f;
+    *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<int64_t>(r) * n_pad + c) = __floats2bfloat162_rn(a, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GRU backward
+__global__ void k_gru_bwd_pre(const float* __restrict__ dh, const bf16* __restrict__ z, const bf16* __restrict__ hc,
+                              const bf16* __restrict__ h, int64_t n4, bf16* __restrict__ dpre_z,
+                              bf16* __restrict__ dpre_h, float* __restrict__ dh_acc) {
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 g = *reinterpret_cast<const float4*>(dh + t * 4);
+    const uint2 zz = *reinterpret_cast<const uint2*>(z + t * 4);
+    const uint2 cc = *reinterpret_cast<const uint2*>(hc + t * 4);
+    const uint2 hh = *reinterpret_cast<const uint2*>(h + t * 4);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+    const float zv[4] = {bf16_lo_f(zz.x), bf16_hi_f(zz.x), bf16_lo_f(zz.y), bf16_hi_f(zz.y)};
+    const float cv[4] = {bf16_lo_f(cc.x), bf16_hi_f(cc.x), bf16_lo_f(cc.y), bf16_hi_f(cc.y)};
+    const float hv[4] = {bf16_lo_f(hh.x), bf16_hi_f(hh.x), bf16_lo_f(hh.y), bf16_hi_f(hh.y)};
+    float dz[4], dc[4], da[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dz[i] = gv[i] * (cv[i] - hv[i]) * zv[i] * (1.f - zv[i]);
+      dc[i] = gv[i] * zv[i] * (1.f - cv[i] * cv[i]);
+      da[i] = gv[i] * (1.f - zv[i]);
+    }
+    *reinterpret_cast<uint2*>(dpre_z + t * 4) = pack4_bf16(dz[0], dz[1], dz[2], dz[3]);
+    *reinterpret_cast<uint2*>(dpre_h + t * 4) = pack4_bf16(dc[0], dc[1], dc[2], dc[3]);
+    *reinterpret_cast<float4*>(dh_acc + t * 4) = make_float4(da[0], da[1], da[2], da[3]);
+  }
+}
+
+// column sums of a bf16 matrix; block = 8 warps x 64 columns, grid = (col chunks, row slabs)
+__global__ void k_colsum(const bf16* __restrict__ X, int64_t ld, int rows, int n_cols, float* __restrict__ out1,
+                         float scale1, float* __restrict__ out2, float scale2) {
+  __shared__ float2 red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + lane * 2;
+  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float2 acc = make_float2(0.f, 0.f);
+  if (c < n_cols) {
+    for (int r = r0 + w; r < r1; r += 8) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(X + static_cast<int64_t>(r) * ld + c);
+      const float2 f = __bfloat1622float2(v);
+      acc.x += f.x;
+      acc.y += f.y;
+    }
+  }
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && c < n_cols) {
+    float2 t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      t.x += red[i][lane].x;
+      t.y += red[i][lane].y;
+    }
+    if (out1 != nullptr) {
+      atomicAdd(out1 + c, t.x * scale1);
+      if (c + 1 < n_cols) atomicAdd(out1 + c + 1, t.y * scale1);
+    }
+    if (out2 != nullptr) {
+      atomicAdd(out2 + c, t.x * scale2);
+      if (c + 1 < n_cols) atomicAdd(out2 + c + 1, t.y * scale2);
+    }
+  }
+}
+
+__global__ void k_node_init_bwd(const float* __restrict__ dh0, const bf16* __restrict__ h0b,
+                                const float* __restrict__ feat, const float* __restrict__ role_emb,
+                                const float* __restrict__ verb_emb, const int64_t* __restrict__ verb,
+                                const int32_t* __restrict__ verb2roles, int n_roles, int B, int R, int D,
+                                float* __restrict__ d_role_emb, float* __restrict__ d_verb_emb) {
+  const int D4 = D / 4;
+  const int64_t total = static_cast<int64_t>(B) * D4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(t / D4);
+    const int d = static_cast<int>(t % D4) * 4;
+    const int64_t v = verb[b];
+    const float4 f = *reinterpret_cast<const float4*>(feat + static_cast<int64_t>(b) * D + d);
+    const float4 ve = *reinterpret_cast<const float4*>(verb_emb + v * D + d);
+    float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < R; ++r) {
+      const int idx = verb2roles[v * R + r];
+      if (idx == n_roles) continue;  // padding_idx row: never receives a gradient, contributes 0 to verb_emb
+      const int64_t off = (static_cast<int64_t>(b) * R + r) * D + d;
+      float4 g = *reinterpret_cast<const float4*>(dh0 + off);
+      const uint2 hb = *reinterpret_cast<const uint2*>(h0b + off);
+      g.x = (bf16_lo_f(hb.x) > 0.f) ? g.x : 0.f;
+      g.y = (bf16_hi_f(hb.x) > 0.f) ? g.y : 0.f;
+      g.z = (bf16_lo_f(hb.y) > 0.f) ? g.z : 0.f;
+      g.w = (bf16_hi_f(hb.y) > 0.f) ? g.w : 0.f;
+      const float4 re = *reinterpret_cast<const float4*>(role_emb + static_cast<int64_t>(idx) * D + d);
+      float* dr = d_role_emb + static_cast<int64_t>(idx) * D + d;
+      atomicAdd(dr + 0, g.x * f.x * ve.x);
+      atomicAdd(dr + 1, g.y * f.y * ve.y);
+      atomicAdd(dr + 2, g.z * f.z * ve.z);
+      atomicAdd(dr + 3, g.w * f.w * ve.w);
+      accv.x = fmaf(g.x * f.x, re.x, accv.x);
+      accv.y = fmaf(g.y * f.y, re.y, accv.y);
+      accv.z = fmaf(g.z * f.z, re.z, accv.z);
+      accv.w = fmaf(g.w * f.w, re.w, accv.w);
+    }
+    float* dv = d_verb_emb + v * D + d;
+    atomicAdd(dv + 0, accv.x);
+    atomicAdd(dv + 1, accv.y);
+    atomicAdd(dv + 2, accv.z);
+    atomicAdd(dv + 3, accv.w);
+  }
+}
+
+__global__ void k_fill_f32(float* p, int64_t n, float v) {
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    p[t] = v;
+}
+
+#define SRG_LAUNCH_CHECK()                                                                      \
+  do {                                                                                          \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess)                                                                      \
+      return set_error(SRG_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ launchers
+int launch_gather_mask(const int32_t* verb2roles, const int32_t* role_count, int n_verbs, int R, const int64_t* verb,
+                       int B, int64_t* role_idx, float* mask, int* bad, cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  k_gather_mask<<<grid_for(static_cast<int64_t>(B) * R * R), kThreads, 0, s>>>(verb2roles, role_count, n_verbs, R,
+                                                                              verb, B, role_idx, mask, bad);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_node_init_noun(const float* feat, const float* role_emb, const float* verb_emb, const int64_t* verb,
+                          const int32_t* verb2roles, int n_verbs, int B, int R, int D, float* h32, bf16* hb_hi,
+                          bf16* hb_lo, cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  k_node_init_noun<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(
+      feat, role_emb, verb_emb, verb, verb2roles, n_verbs, B, R, D, h32, hb_hi, hb_lo);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_node_init_verb(const float* feat, int B, int D, float* h32, bf16* hb_hi, bf16* hb_lo, cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  const int64_t n4 = static_cast<int64_t>(B) * D / 4;
+  k_node_init_verb<<<grid_for(n4), kThreads, 0, s>>>(feat, n4, h32, hb_hi, hb_lo);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_split_cast(const float* x, int64_t n, bf16* hi, bf16* lo, cudaStream_t s) {
+  if (n <= 0) return SRG_OK;
+  k_split_cast<<<grid_for(n / 4), kThreads, 0, s>>>(x, n / 4, hi, lo);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_aggregate(const float* h32, const float* mask, int B, int R, int D, bf16* a_hi, bf16* a_lo,
+                     cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
+  k_aggregate<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(h32, mask, B, R, D, a_hi, a_lo);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_aggregate_bwd(const float* dh_acc, const float* da, const float* mask, int B, int R, int D, float* dh,
+                         cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
+  k_aggregate_bwd<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(dh_acc, da, mask, B, R, D, dh);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_pack_weight(const float* src, int rows, int cols, int rows_pad, bf16* dst, int64_t ld_dst, int64_t col_off,
+                       int want_lo, cudaStream_t s) {
+  k_pack_weight<<<grid_for(static_cast<int64_t>(rows_pad) * cols / 2), kThreads, 0, s>>>(src, rows, cols, rows_pad,
+                                                                                        dst, ld_dst, col_off, want_lo);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_pack_bias(const float* a, const float* b, int n, int n_pad, float* dst, cudaStream_t s) {
+  k_pack_bias<<<grid_for(n_pad), kThreads, 0, s>>>(a, b, n, n_pad, dst);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_dropout_cast(const float* h32, const uint8_t* keep, float scale, int64_t n, bf16* hi, bf16* lo,
+                        cudaStream_t s) {
+  if (n <= 0) return SRG_OK;
+  k_dropout_cast<<<grid_for(n / 4), kThreads, 0, s>>>(h32, keep, scale, n / 4, hi, lo);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_dropout_bwd(const float* dx, const uint8_t* keep, float scale, int64_t n, float* dh, cudaStream_t s) {
+  if (n <= 0) return SRG_OK;
+  k_dropout_bwd<<<grid_for(n / 4), kThreads, 0, s>>>(dx, keep, scale, n / 4, dh);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_count_targets(const int64_t* gt, int B, int R, int ignore_index, float* counts, cudaStream_t s) {
+  SRG_CUDA(cudaMemsetAsync(counts, 0, 3 * sizeof(float), s));
+  if (B <= 0) return SRG_OK;
+  k_count_targets<<<grid_for(static_cast<int64_t>(B) * 3 * R, kThreads, 148), kThreads, 0, s>>>(gt, B, R, ignore_index,
+                                                                                               counts);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_t* gt, int B, int R,
+                    const float* counts, float* loss, float* dlogits, float grad_scale, cudaStream_t s) {
+  const int rows = B * R;
+  if (rows <= 0) return SRG_OK;
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_cross_entropy<3><<<blocks, kThreads, 0, s>>>(logits, ldl, n_labels, rows, gt, R, n_labels, counts, 0.f, loss,
+                                                dlogits, grad_scale);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t* gt, int B, float inv_batch,
+                   float* loss, float* dlogits, float grad_scale, cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  int blocks = (B + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_cross_entropy<1><<<blocks, kThreads, 0, s>>>(logits, ldl, n_verbs, B, gt, 1, -100, nullptr, inv_batch, loss,
+                                                dlogits, grad_scale);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, cudaStream_t s) {
+  if (rows <= 0) return SRG_OK;
+  k_cast_pad<<<grid_for(static_cast<int64_t>(rows) * n_pad / 2), kThreads, 0, s>>>(src, ld, rows, n_valid, n_pad, dst);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_gru_bwd_pre(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int64_t n, bf16* dpre_z,
+                       bf16* dpre_h, float* dh_acc, cudaStream_t s) {
+  if (n <= 0) return SRG_OK;
+  k_gru_bwd_pre<<<grid_for(n / 4), kThreads, 0, s>>>(dh, z, hc, h, n / 4, dpre_z, dpre_h, dh_acc);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_colsum(const bf16* X, int64_t ld, int rows, int n_cols, float* out1, float scale1, float* out2,
+                  float scale2, cudaStream_t s) {
+  if (rows <= 0 || n_cols <= 0) return SRG_OK;
+  int slabs = (rows + 255) / 256;
+  if (slabs > 64) slabs = 64;
+  dim3 grid((n_cols + 63) / 64, slabs);
+  k_colsum<<<grid, kThreads, 0, s>>>(X, ld, rows, n_cols, out1, scale1, out2, scale2);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, const float* role_emb,
+                         const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_roles, int B,
+                         int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  k_node_init_bwd<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(
+      dh0, h0b, feat, role_emb, verb_emb, verb, verb2roles, n_roles, B, R, D, d_role_emb, d_verb_emb);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s) {
+  if (n <= 0) return SRG_OK;
+  k_fill_f32<<<grid_for(n), kThreads, 0, s>>>(p, n, v);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+}  // namespace srg

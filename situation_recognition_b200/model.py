@@ -1,0 +1,459 @@
+"""Drop-in host side of the reference's `model.py` for the GGNN role-graph stage.
+
+`FCGGNN(encoder, D_hidden_state)` keeps the reference's constructor, attribute / parameter names (= checkpoint
+keys), `forward(img, gt_verb)`, `predict_verb`, `predict_nouns`, `verb_loss`, `nouns_loss` (model.py:90-201) and
+`GGSNN(layersize).forward(hidden_state, mask, verb)` (model.py:38-86).  The arithmetic of the stage runs in
+libsrggnn.so (hand-written sm_100a kernels) through ctypes; PyTorch only owns memory, streams and autograd
+bookkeeping.  There is no CPU / eager fallback: non-CUDA inputs raise.
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * logits are returned in fp32 as `[..., :n]` views of buffers padded to a multiple of 256 columns;
+  * on CUDA the reference always runs under fp16 autocast; this module computes with bf16 tensor-core operands and
+    fp32 accumulation/state (`precision="bf16"`), or a 3-term bf16 split that meets fp32 parity
+    (`precision="fp32"`, forward only);
+  * `model.module` returns the model itself so that unmodified `sr.py` CUDA branches (`model.module.verb_loss`)
+    keep working without `nn.DataParallel`.
+"""
+import ctypes
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import SRG_MODE_NOUN, SRG_MODE_VERB, SRG_PREC_BF16, SRG_PREC_FP32
+from .imsitu_encoder import tables_from_encoder
+
+T_STEPS = 4  # model.py:60
+
+
+def _pad256(n):
+    return (n + 255) // 256 * 256
+
+
+class resnet(nn.Module):
+    """Frozen torchvision ResNet-152 returning the 2048-d pooled features (model.py:8-35).  Stock library module,
+    not part of the CUDA path; timed separately.  Offline, the pretrained weights cannot be downloaded, so
+    `pretrained=None` tries and falls back to random init with a warning."""
+
+    def __init__(self, out_layers, pretrained=None):
+        super().__init__()
+        import torchvision as tv
+        weights = None
+        if pretrained is None or pretrained:
+            try:
+                self.model = tv.models.resnet152(weights=tv.models.ResNet152_Weights.IMAGENET1K_V1, progress=False)
+                weights = "imagenet"
+            except Exception as e:  # no network / no cached checkpoint
+                if pretrained:
+                    raise
+                warnings.warn("pretrained ResNet-152 weights unavailable (%s); using random init" % type(e).__name__)
+        if weights is None:
+            self.model = tv.models.resnet152(weights=None)
+        for p in self.model.parameters():
+            p.requires_grad = False
+        self.model.fc = nn.Identity()
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class _Engine:
+    """Owns the libsrggnn handle of one model on one device and keeps the packed bf16 weights in sync."""
+
+    def __init__(self, model, device):
+        self.lib = _lib.load()
+        enc = model.encoder
+        self.D = model.D
+        self.R = enc.get_max_role_count()
+        self.V, self.NR, self.L = enc.get_num_verbs(), enc.get_num_roles(), enc.get_num_labels()
+        self.Vpad, self.Lpad = _pad256(self.V), _pad256(self.L)
+        self.device = device
+        h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.srg_create(ctypes.byref(h), device.index if device.index is not None else
+                                           torch.cuda.current_device(), self.D, self.R, T_STEPS, self.V, self.NR,
+                                           self.L))
+        self.h = h
+        v2r, rc = tables_from_encoder(enc)
+        _lib.check(self.lib.srg_set_tables(self.h, v2r.ctypes.data_as(ctypes.c_void_p),
+                                           rc.ctypes.data_as(ctypes.c_void_p)))
+        self._packed_key = None
+        self.launches = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.srg_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_cta_group(self, cg):
+        _lib.check(self.lib.srg_set_cta_group(self.h, cg))
+
+    def param_list(self, model):
+        g = model.ggsnn
+        return [g.W_p.weight, g.W_p.bias, g.W_z.weight, g.W_z.bias, g.U_z.weight, g.U_z.bias,
+                g.W_r.weight, g.W_r.bias, g.U_r.weight, g.U_r.bias, g.W_h.weight, g.W_h.bias,
+                g.U_h.weight, g.U_h.bias,
+                model.verb_classifier[1].weight, model.verb_classifier[1].bias,
+                model.nouns_classifier[1].weight, model.nouns_classifier[1].bias]
+
+    def ensure_packed(self, model, prec):
+        params = self.param_list(model)
+        key = (prec,) + tuple((p.data_ptr(), p._version) for p in params)
+        if key == self._packed_key:
+            return
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != self.device:
+                raise _lib.SrgError("GGNN parameters must be contiguous fp32 tensors on %s" % self.device)
+        sp = _lib.SrgParams(*[ctypes.c_void_p(p.data_ptr()) for p in params])
+        _lib.check(self.lib.srg_pack_weights(self.h, ctypes.byref(sp), prec, _lib.stream_ptr()))
+        self._packed_key = key
+
+    def workspace(self, mode, B, prec, save):
+        n = self.lib.srg_workspace_bytes(self.h, mode, B, prec, int(save))
+        return torch.empty(n, dtype=torch.uint8, device=self.device)
+
+
+def _prec_code(name):
+    if name in ("bf16", SRG_PREC_BF16):
+        return SRG_PREC_BF16
+    if name in ("fp32", SRG_PREC_FP32):
+        return SRG_PREC_FP32
+    raise ValueError("precision must be 'bf16' or 'fp32'")
+
+
+def _as_feat(x, D):
+    if not x.is_cuda:
+        raise _lib.SrgError("the GGNN stage has no CPU path: features must be CUDA tensors")
+    x = x.reshape(x.shape[0], -1)
+    if x.shape[1] != D:
+        raise _lib.SrgError("backbone features have %d channels, expected %d" % (x.shape[1], D))
+    return x.detach().float().contiguous()
+
+
+def _grad_struct(named, engine):
+    """Zero-initialised fp32 gradient buffers + the srg_grads struct pointing at them."""
+    fields = {}
+    for n in _lib._PARAM_FIELDS + ["role_emb", "verb_emb"]:
+        t = named.get(n)
+        fields[n] = ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    return _lib.SrgGrads(**fields)
+
+
+_GGNN_FIELDS = _lib._PARAM_FIELDS[:14]
+
+
+class _NounsStage(torch.autograd.Function):
+    """predict_nouns minus the backbone (model.py:117-155)."""
+
+    @staticmethod
+    def forward(ctx, model, grad_on, feat, verb, keep, role_emb, verb_emb, *params):
+        eng = model._engine_for(feat.device)
+        prec = _prec_code(model.precision)
+        B = feat.shape[0]
+        need_grad = grad_on and any(ctx.needs_input_grad)
+        if need_grad and prec != SRG_PREC_BF16:
+            raise _lib.SrgError("precision='fp32' is a forward-only parity mode; use torch.no_grad() or precision='bf16'")
+        eng.ensure_packed(model, prec)
+        drop_p = model.drop_p if keep is not None else 0.0
+        logits = torch.empty(B * eng.R, eng.Lpad, dtype=torch.float32, device=feat.device)
+        ws = eng.workspace(SRG_MODE_NOUN, B, prec, need_grad)
+        verb = verb.detach().to(torch.int64).contiguous()
+        _lib.check(eng.lib.srg_nouns_forward(eng.h, _lib.ptr(feat), _lib.ptr(verb), B, _lib.ptr(role_emb),
+                                             _lib.ptr(verb_emb), _lib.ptr(keep), drop_p, _lib.ptr(logits), eng.Lpad,
+                                             prec, int(need_grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        if need_grad:
+            ctx.eng, ctx.ws, ctx.B, ctx.drop_p = eng, ws, B, drop_p
+            ctx.save_for_backward(feat, verb, keep, role_emb, verb_emb, *params)
+        return logits.view(B, eng.R, eng.Lpad)[:, :, :eng.L]
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        eng = ctx.eng
+        feat, verb, keep, role_emb, verb_emb, *params = ctx.saved_tensors
+        B = ctx.B
+        dl, ldl = _padded_grad(dlogits.reshape(B * eng.R, eng.L), eng.Lpad)
+        grads = {n: torch.zeros_like(p) for n, p in zip(_GGNN_FIELDS + ["Wc_noun", "bc_noun"], params)}
+        grads["role_emb"] = torch.zeros_like(role_emb)
+        grads["verb_emb"] = torch.zeros_like(verb_emb)
+        sg = _grad_struct(grads, eng)
+        _lib.check(eng.lib.srg_nouns_backward(eng.h, _lib.ptr(dl), ldl, _lib.ptr(feat), _lib.ptr(verb), B,
+                                              _lib.ptr(role_emb), _lib.ptr(verb_emb), _lib.ptr(keep), ctx.drop_p,
+                                              ctypes.byref(sg), _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()))
+        ctx.ws = None
+        out = [grads[n] for n in _GGNN_FIELDS + ["Wc_noun", "bc_noun"]]
+        return (None, None, None, None, None, grads["role_emb"], grads["verb_emb"], *out)
+
+
+class _VerbStage(torch.autograd.Function):
+    """predict_verb minus the backbone (model.py:160-168)."""
+
+    @staticmethod
+    def forward(ctx, model, grad_on, feat, keep, *params):
+        eng = model._engine_for(feat.device)
+        prec = _prec_code(model.precision)
+        B = feat.shape[0]
+        need_grad = grad_on and any(ctx.needs_input_grad)
+        if need_grad and prec != SRG_PREC_BF16:
+            raise _lib.SrgError("precision='fp32' is a forward-only parity mode; use torch.no_grad() or precision='bf16'")
+        eng.ensure_packed(model, prec)
+        drop_p = model.drop_p if keep is not None else 0.0
+        logits = torch.empty(B, eng.Vpad, dtype=torch.float32, device=feat.device)
+        ws = eng.workspace(SRG_MODE_VERB, B, prec, need_grad)
+        _lib.check(eng.lib.srg_verb_forward(eng.h, _lib.ptr(feat), B, _lib.ptr(keep), drop_p, _lib.ptr(logits),
+                                            eng.Vpad, prec, int(need_grad), _lib.ptr(ws), ws.numel(),
+                                            _lib.stream_ptr()))
+        if need_grad:
+            ctx.eng, ctx.ws, ctx.B, ctx.drop_p = eng, ws, B, drop_p
+            ctx.save_for_backward(keep, *params)
+        return logits[:, :eng.V]
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        eng = ctx.eng
+        keep, *params = ctx.saved_tensors
+        B = ctx.B
+        dl, ldl = _padded_grad(dlogits.reshape(B, eng.V), eng.Vpad)
+        grads = {n: torch.zeros_like(p) for n, p in zip(_GGNN_FIELDS + ["Wc_verb", "bc_verb"], params)}
+        sg = _grad_struct(grads, eng)
+        _lib.check(eng.lib.srg_verb_backward(eng.h, _lib.ptr(dl), ldl, B, _lib.ptr(keep), ctx.drop_p, ctypes.byref(sg),
+                                             _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()))
+        ctx.ws = None
+        return (None, None, None, None, *[grads[n] for n in _GGNN_FIELDS + ["Wc_verb", "bc_verb"]])
+
+
+def _padded_grad(g, npad):
+    """fp32 [rows, n] gradient with unit column stride and a 16-byte aligned row pitch (no copy when the autograd
+    engine hands back the padded view produced by the loss kernels)."""
+    if g.dtype == torch.float32 and g.dim() == 2 and g.stride(1) == 1 and g.stride(0) >= g.shape[1] and \
+            g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0:
+        return g, g.stride(0)
+    buf = torch.zeros(g.shape[0], npad, dtype=torch.float32, device=g.device)
+    buf[:, :g.shape[1]] = g
+    return buf, npad
+
+
+def _rows_view(logits, n):
+    """[rows, n] view with unit column stride of a [..., n] logits tensor, and its leading dimension."""
+    x = logits
+    if x.dtype != torch.float32:
+        x = x.float()
+    lead = x.shape[:-1]
+    ok = x.stride(-1) == 1
+    ld = x.stride(-2) if x.dim() >= 2 else n
+    if ok and x.dim() == 3:
+        ok = x.stride(0) == x.shape[1] * ld
+    if not ok or ld < n:
+        x = x.contiguous()
+        ld = n
+    rows = 1
+    for s in lead:
+        rows *= s
+    return x, rows, ld
+
+
+class _NounsLoss(torch.autograd.Function):
+    """FCGGNN.nouns_loss (model.py:189-201): forward computes the loss and d(loss)/d(logits) in one pass."""
+
+    @staticmethod
+    def forward(ctx, model, grad_on, logits, gt_nouns):
+        eng = model._engine_for(logits.device)
+        x, rows, ld = _rows_view(logits, eng.L)
+        B = rows // eng.R
+        gt = gt_nouns.detach().to(torch.int64).contiguous()
+        counts = torch.empty(3, dtype=torch.float32, device=logits.device)
+        _lib.check(eng.lib.srg_count_targets(eng.h, _lib.ptr(gt), B, _lib.ptr(counts), _lib.stream_ptr()))
+        if model.loss_group is not None:
+            torch.distributed.all_reduce(counts, group=model.loss_group)
+        loss = torch.zeros((), dtype=torch.float32, device=logits.device)
+        need_grad = grad_on and ctx.needs_input_grad[2]
+        dl = torch.empty(rows, ld, dtype=torch.float32, device=logits.device) if need_grad else None
+        _lib.check(eng.lib.srg_nouns_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts), _lib.ptr(loss),
+                                          _lib.ptr(dl), 1.0, _lib.stream_ptr()))
+        if need_grad:
+            ctx.save_for_backward(dl)
+            ctx.shape = tuple(logits.shape)
+            ctx.n = eng.L
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dl,) = ctx.saved_tensors
+        g = dl if _is_one(gout) else dl * gout
+        return None, None, g[:, :ctx.n].view(ctx.shape), None
+
+
+class _VerbLoss(torch.autograd.Function):
+    """FCGGNN.verb_loss (model.py:182-187)."""
+
+    @staticmethod
+    def forward(ctx, model, grad_on, logits, gt_verb):
+        eng = model._engine_for(logits.device)
+        x, rows, ld = _rows_view(logits, eng.V)
+        gt = gt_verb.detach().to(torch.int64).contiguous()
+        world = 1
+        if model.loss_group is not None:
+            world = torch.distributed.get_world_size(model.loss_group)
+        loss = torch.zeros((), dtype=torch.float32, device=logits.device)
+        need_grad = grad_on and ctx.needs_input_grad[2]
+        dl = torch.empty(rows, ld, dtype=torch.float32, device=logits.device) if need_grad else None
+        _lib.check(eng.lib.srg_verb_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, 1.0 / (rows * world),
+                                         _lib.ptr(loss), _lib.ptr(dl), 1.0, _lib.stream_ptr()))
+        if need_grad:
+            ctx.save_for_backward(dl)
+            ctx.shape = tuple(logits.shape)
+            ctx.n = eng.V
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dl,) = ctx.saved_tensors
+        g = dl if _is_one(gout) else dl * gout
+        return None, None, g[:, :ctx.n].view(ctx.shape), None
+
+
+def _is_one(g):
+    return False  # keep the general path; a fused scale is a later optimisation
+
+
+class GGSNN(nn.Module):
+    """Parameter container + drop-in forward of the reference's GGSNN (model.py:38-86)."""
+
+    def __init__(self, layersize):
+        super().__init__()
+        self.W_p = nn.Linear(layersize, layersize)
+        self.W_z = nn.Linear(layersize, layersize)
+        self.U_z = nn.Linear(layersize, layersize)
+        self.W_r = nn.Linear(layersize, layersize)
+        self.U_r = nn.Linear(layersize, layersize)
+        self.W_h = nn.Linear(layersize, layersize)
+        self.U_h = nn.Linear(layersize, layersize)
+        self._owner = None
+
+    def forward(self, hidden_state, mask=None, verb=False):
+        """Forward-only (inference) entry with the reference signature; training goes through FCGGNN."""
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise _lib.SrgError("GGSNN.forward needs the owning FCGGNN (it holds the CUDA engine)")
+        return owner._ggsnn_forward(hidden_state, mask, verb)
+
+
+class FCGGNN(nn.Module):
+    def __init__(self, encoder, D_hidden_state, backbone="resnet152", precision="bf16", pretrained=None):
+        super().__init__()
+        self.encoder = encoder
+        self.D = D_hidden_state
+        self.precision = precision
+        self.drop_p = 0.5
+        self.loss_group = None          # torch.distributed group over which loss denominators are global
+        self.dropout_masks = None       # optional (verb, pred-noun, gt-noun) uint8 keep-masks for parity tests
+        self.role_emb = nn.Embedding(encoder.get_num_roles() + 1, D_hidden_state, padding_idx=encoder.get_num_roles())
+        self.verb_emb = nn.Embedding(encoder.get_num_verbs(), D_hidden_state)
+        if backbone == "resnet152":
+            self.convnet_verbs = resnet(encoder.get_num_verbs(), pretrained)
+            self.convnet_nouns = resnet(encoder.get_num_labels(), pretrained)
+        else:  # GGNN-stage benchmarks / tests: `img` already holds the [B, D] backbone features
+            self.convnet_verbs = nn.Identity()
+            self.convnet_nouns = nn.Identity()
+        self.ggsnn = GGSNN(layersize=D_hidden_state)
+        self.verb_classifier = nn.Sequential(nn.Dropout(self.drop_p), nn.Linear(D_hidden_state, encoder.get_num_verbs()))
+        self.nouns_classifier = nn.Sequential(nn.Dropout(self.drop_p), nn.Linear(D_hidden_state, encoder.get_num_labels()))
+        import weakref
+        self.ggsnn._owner = weakref.ref(self)
+        self._engines = {}
+
+    # sr.py accesses model.module.* when CUDA is available (DataParallel wrapper in the reference)
+    @property
+    def module(self):
+        return self
+
+    def _engine_for(self, device):
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _Engine(self, torch.device("cuda", key[1]))
+            self._engines[key] = eng
+        return eng
+
+    def _ggnn_params(self):
+        g = self.ggsnn
+        return [g.W_p.weight, g.W_p.bias, g.W_z.weight, g.W_z.bias, g.U_z.weight, g.U_z.bias, g.W_r.weight, g.W_r.bias,
+                g.U_r.weight, g.U_r.bias, g.W_h.weight, g.W_h.bias, g.U_h.weight, g.U_h.bias]
+
+    def _keep_mask(self, which, rows, device):
+        if not self.training:
+            return None
+        if self.dropout_masks is not None:
+            m = self.dropout_masks[which]
+            return None if m is None else m.to(device=device, dtype=torch.uint8).contiguous()
+        return torch.empty(rows, self.D, dtype=torch.uint8, device=device).bernoulli_(1.0 - self.drop_p)
+
+    # ---- reference API -------------------------------------------------------------------------
+    def predict_nouns(self, img, gt_verb, batch_size, _mask_slot=1):
+        feat = _as_feat(self.convnet_nouns(img), self.D)
+        if feat.shape[0] != batch_size:
+            raise _lib.SrgError("batch_size %d does not match the features (%d)" % (batch_size, feat.shape[0]))
+        keep = self._keep_mask(_mask_slot, batch_size * self.encoder.get_max_role_count(), feat.device)
+        gt_verb = gt_verb.to(feat.device)
+        return _NounsStage.apply(self, torch.is_grad_enabled(), feat, gt_verb, keep, self.role_emb.weight, self.verb_emb.weight,
+                                 *self._ggnn_params(), self.nouns_classifier[1].weight, self.nouns_classifier[1].bias)
+
+    def predict_verb(self, img, batch_size):
+        feat = _as_feat(self.convnet_verbs(img), self.D)
+        if feat.shape[0] != batch_size:
+            raise _lib.SrgError("batch_size %d does not match the features (%d)" % (batch_size, feat.shape[0]))
+        keep = self._keep_mask(0, batch_size, feat.device)
+        return _VerbStage.apply(self, torch.is_grad_enabled(), feat, keep, *self._ggnn_params(), self.verb_classifier[1].weight,
+                                self.verb_classifier[1].bias)
+
+    def forward(self, img, gt_verb, img_nouns=None):
+        """model.py:171-180.  `img_nouns` (extension) lets benchmarks feed different synthetic features to the verb
+        and noun paths, as the two backbones would produce."""
+        batch_size = img.size(0)
+        pred_verb = self.predict_verb(img, batch_size)
+        img_n = img if img_nouns is None else img_nouns
+        pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1)
+        gt_pred_nouns = self.predict_nouns(img_n, gt_verb, batch_size, _mask_slot=2)
+        return pred_verb, pred_nouns, gt_pred_nouns
+
+    def verb_loss(self, pred_verb, gt_verb):
+        return _VerbLoss.apply(self, torch.is_grad_enabled(), pred_verb, gt_verb.to(pred_verb.device))
+
+    def nouns_loss(self, pred_nouns, gt_nouns):
+        return _NounsLoss.apply(self, torch.is_grad_enabled(), pred_nouns, gt_nouns.to(pred_nouns.device))
+
+    # ---- GGSNN.forward drop-in (inference) ------------------------------------------------------
+    def _ggsnn_forward(self, hidden_state, mask=None, verb=False):
+        if not hidden_state.is_cuda:
+            raise _lib.SrgError("the GGNN stage has no CPU path: hidden_state must be a CUDA tensor")
+        eng = self._engine_for(hidden_state.device)
+        prec = _prec_code(self.precision)
+        eng.ensure_packed(self, prec)
+        h = hidden_state.detach().float().contiguous().clone()
+        if verb:
+            B, mode, mk = h.shape[0], SRG_MODE_VERB, None
+        else:
+            B, mode = mask.shape[0], SRG_MODE_NOUN
+            mk = mask.detach().to(device=h.device, dtype=torch.float32).contiguous()
+        ws = eng.workspace(mode, B, prec, False)
+        _lib.check(eng.lib.srg_ggnn_forward(eng.h, mode, _lib.ptr(h), _lib.ptr(mk), B, prec, 0, _lib.ptr(ws),
+                                            ws.numel(), _lib.stream_ptr()))
+        return h
+
+    def gather_mask(self, verbs):
+        """CUDA replacement of encoder.get_role_ids_batch + get_adj_matrix_noself (imsitu_encoder.py:172-180,209-229)."""
+        if not verbs.is_cuda:
+            raise _lib.SrgError("gather_mask needs a CUDA tensor of verb ids")
+        eng = self._engine_for(verbs.device)
+        v = verbs.detach().to(torch.int64).contiguous()
+        B = v.shape[0]
+        R = eng.R
+        role_idx = torch.empty(B, R, dtype=torch.int64, device=v.device)
+        mask = torch.empty(B, R, R, dtype=torch.float32, device=v.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=v.device)
+        _lib.check(eng.lib.srg_gather_mask(eng.h, _lib.ptr(v), B, _lib.ptr(role_idx), _lib.ptr(mask), _lib.ptr(bad),
+                                           _lib.stream_ptr()))
+        return role_idx, mask, bad
