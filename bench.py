@@ -1,0 +1,324 @@
+"""Headline benchmark: GGNN role-graph stage, images/sec forward+backward (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W     # CPU arm: the oracle port of the reference
+
+Workload (BASELINE.json configs[2]/[3]): one training step of the GGNN stage at global batch 6144, D=2048,
+504 verbs / 190 roles / 2001 labels / 6 roles, synthetic backbone features and labels, random-init weights:
+verb path + predicted-verb noun path + gt-verb noun path forward, the three losses, backward of
+verb_loss + nouns_loss (sr.py:63-79), gradient all-reduce when N > 1, clip_grad_norm_(1) + Adamax (sr.py:80-83).
+The batch is sharded over the N GPUs (strong scaling, as BASELINE.json states it).  Prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_IMAGE_FWD_BWD = 6.547e9   # BASELINE.md section 3 (algorithmic, aggregate-then-project)
+METRIC = "ggnn_images_per_sec_fwd_bwd"
+UNIT = "images/s"
+D = 2048
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_sustained": d.get("bf16_tflops_sustained", 1396.2), "bf16_burst": d.get("bf16_tflops", 1658.8),
+                "hbm_gbs": d.get("hbm_gbs", 6550.4), "source": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # samples under load = the upper half (the sampler also sees the idle edges of the region)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_setup(B, seed=1234):
+    import torch
+    from oracle import ggnn_oracle as O
+    from situation_recognition_b200.imsitu_encoder import imsitu_encoder
+    from situation_recognition_b200.synthetic import make_batch, make_train_json
+    enc = imsitu_encoder(make_train_json(seed=0), verbose=False)
+    params = O.init_params(enc.get_num_verbs(), enc.get_num_roles(), enc.get_num_labels(), D, seed=0)
+    batch = make_batch(enc, B, D, seed=seed)
+    tables = O.build_tables(enc.roles_per_verb, enc.verb_list, enc.role_list)
+    return O, enc, params, batch, tables
+
+
+def oracle_step(O, enc, params, batch, tables):
+    fv, fn, gt_verb, gt_nouns = batch
+    t, c = tables
+    return O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, enc.get_num_labels())
+
+
+def cpu_baseline(budget_s=20.0):
+    """The oracle port of the reference's fwd+bwd step, timed on this host's cores on a bounded sample."""
+    import torch
+    B = 32
+    O, enc, params, batch, tables = oracle_setup(B)
+    t0 = time.time()
+    oracle_step(O, enc, params, batch, tables)
+    t1 = time.time() - t0
+    # pick a sample that fills roughly the budget
+    per_img = t1 / B
+    Bs = int(max(32, min(256, (budget_s / 2) / max(per_img, 1e-6))) // 8 * 8)
+    O, enc, params, batch, tables = oracle_setup(Bs)
+    t0 = time.time()
+    oracle_step(O, enc, params, batch, tables)
+    dt = time.time() - t0
+    return {"value": Bs / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "1 fwd+bwd step of the oracle port (reference arithmetic as written, fp32) on %d images; "
+                      "os.cpu_count()=%s" % (Bs, os.cpu_count())}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    steps, warmup = args.steps, args.warmup
+    O, enc, params, batch, tables = oracle_setup(8)
+    t0 = time.time()
+    oracle_step(O, enc, params, batch, tables)
+    per_img = (time.time() - t0) / 8
+    budget = 150.0
+    Bs = int(max(8, min(256, budget / max(1, steps + warmup) / max(per_img, 1e-6))) // 8 * 8)
+    O, enc, params, batch, tables = oracle_setup(Bs)
+    for _ in range(warmup):
+        oracle_step(O, enc, params, batch, tables)
+    t0 = time.time()
+    for _ in range(steps):
+        oracle_step(O, enc, params, batch, tables)
+    dt = (time.time() - t0) / max(1, steps)
+    value = Bs / dt
+    cb = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+          "sample": "each step = fwd+bwd of the oracle port on %d images (bounded sample of the 6144-image step)" % Bs}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ggnn_stage_fwd_bwd", "global_batch": args.batch, "sample_batch": Bs, "D": D,
+                       "verbs": 504, "roles": 190, "labels": 2001, "max_roles": 6, "T": 4},
+            "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import situation_recognition_b200 as S
+    from situation_recognition_b200 import _lib, parallel
+    from situation_recognition_b200.synthetic import make_batch, make_train_json
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the GGNN stage (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    enc = S.imsitu_encoder(make_train_json(seed=0), verbose=False)
+    torch.manual_seed(0)
+    model = S.FCGGNN(enc, D, backbone=None, precision="bf16").to(dev)
+    model.train()
+    if args.cta_group:
+        model._engine_for(dev).set_cta_group(args.cta_group)
+    flat = parallel.attach(model)
+    opt = torch.optim.Adamax(model.parameters(), lr=0.002)      # sr.py:472-473
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    Bg = args.batch
+    lo, hi = parallel.shard_range(Bg, rank, world)
+    Bl = hi - lo
+    fv, fn, gt_verb, gt_nouns = make_batch(enc, Bg, D, seed=1234)
+    host = [x[lo:hi].contiguous().pin_memory() for x in (fv, fn, gt_verb, gt_nouns)]
+    resident = [x.to(dev, non_blocking=True) for x in host]
+    h2d_bytes = sum(x.numel() * x.element_size() for x in host)
+
+    def step(inputs):
+        a, b, v, n = inputs
+        flat.zero()
+        pred_verb, pred_nouns, gt_pred_nouns = model(a, v, img_nouns=b)
+        vl = model.verb_loss(pred_verb, v)
+        nl = model.nouns_loss(pred_nouns, n)
+        gl = model.nouns_loss(gt_pred_nouns, n)                # logged, never back-propagated (sr.py:70,76)
+        (vl + nl).backward()
+        flat.all_reduce()
+        torch.nn.utils.clip_grad_norm_(params, 1)               # sr.py:81
+        opt.step()
+        return torch.stack([vl.detach(), nl.detach(), gl.detach()])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(3, args.warmup)):
+        step(resident)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.srg_launch_count()
+    total_ms = timed(lambda: step(resident), args.steps)
+    launches = (lib.srg_launch_count() - n0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = Bg / ms_per_step * 1e3
+
+    # ---- dominant kernel, timed live with CUDA events on the launching stream (second pass, same steps)
+    kinds = 32
+    ms_k = (ctypes.c_double * kinds)()
+    fl_k = (ctypes.c_double * kinds)()
+    ct_k = (ctypes.c_longlong * kinds)()
+    barrier()
+    lib.srg_profile_begin()
+    for _ in range(args.steps):
+        step(resident)
+    _lib.check(lib.srg_profile_end(kinds, ms_k, fl_k, ct_k))
+    peaks = load_peaks()
+    per_kind = []
+    for k in range(kinds):
+        if ct_k[k] > 0:
+            per_kind.append({"kernel": lib.srg_profile_kind_name(k).decode(), "launches_per_step": ct_k[k] / args.steps,
+                             "ms_per_step": ms_k[k] / args.steps,
+                             "tflops": fl_k[k] / max(ms_k[k], 1e-9) / 1e9})
+    per_kind.sort(key=lambda d: -d["ms_per_step"])
+    top = per_kind[0]
+    gemm_ms = sum(d["ms_per_step"] for d in per_kind)
+    roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": peaks["bf16_sustained"],
+                "unit": "TFLOP/s", "frac": top["tflops"] / peaks["bf16_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + " (sustained bf16; burst %.1f)" % peaks["bf16_burst"],
+                "launch_ms": top["ms_per_step"] / top["launches_per_step"],
+                "share_of_step": top["ms_per_step"] / ms_per_step,
+                "step_tflops_algorithmic": value * FLOP_PER_IMAGE_FWD_BWD / 1e12,
+                "step_frac": value * FLOP_PER_IMAGE_FWD_BWD / 1e12 / peaks["bf16_sustained"],
+                "gemm_share_of_step": gemm_ms / ms_per_step, "kernels": per_kind[:8]}
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    losses_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        dev_in = [x.to(dev, non_blocking=True) for x in host]
+        out = step(dev_in)
+        losses_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller reads the losses (sr.py:88-90 .item())
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e = {"value": Bg / e2e_ms * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
+           "d2h_bytes_per_step": 12 * world, "ms_per_step": e2e_ms}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "ggnn_stage_fwd_bwd (BASELINE.json configs[2]; sharded = configs[3])",
+                           "global_batch": Bg, "per_gpu_batch": Bl, "D": D, "verbs": 504, "roles": 190, "labels": 2001,
+                           "max_roles": 6, "T": 4, "parallelism": "dp%d" % world,
+                           "step": "zero_grad+fwd(verb,pred-noun,gt-noun)+3 losses+bwd+allreduce+clip+adamax",
+                           "l2": "working set per step (GBs of activations) >> 126 MB L2; no explicit flush",
+                           "weights": "random-init (reference default init)", "dropout": "train mode, p=0.5"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches / args.steps) if args.steps else 0,
+                "roofline": roofline}
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=6144, help="global batch (BASELINE.json: 6144)")
+    ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

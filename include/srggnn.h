@@ -127,6 +127,13 @@ int srg_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t l
                   int c_dtype, int M, int N, int K, const float* bias, float alpha, int cta_group, int k_splits,
                   int reduce, void* stream);
 
+/* Accounting used by bench.py: number of kernels this library has launched so far, and an optional CUDA-event
+ * bracket around every tensor-core GEMM launch, accumulated per kernel kind (kind = 4*epilogue + 2*a_mn + b_mn). */
+long long srg_launch_count(void);
+int srg_profile_begin(void);
+int srg_profile_end(int max_kinds, double* ms, double* flops, long long* launches);
+const char* srg_profile_kind_name(int kind);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,10 @@ SIGNATURES = {
     "srg_nouns_backward": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _c.POINTER(SrgGrads), _vp, _sz,
                                 _vp]),
     "srg_verb_backward": (_i, [_vp, _vp, _i64, _i, _vp, _f, _c.POINTER(SrgGrads), _vp, _sz, _vp]),
+    "srg_launch_count": (_c.c_longlong, []),
+    "srg_profile_begin": (_i, []),
+    "srg_profile_end": (_i, [_i, _vp, _vp, _vp]),
+    "srg_profile_kind_name": (_c.c_char_p, [_i]),
     "srg_gemm_bf16": (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _f, _i, _i, _i, _vp]),
 }
 

@@ -23,6 +23,45 @@ extern "C" {
 
 const char* srg_last_error(void) { return g_last_error; }
 
+long long srg_launch_count(void) { return g_launches.load(); }
+
+int srg_profile_begin(void) {
+  g_prof.n = 0;
+  g_prof.enabled = true;
+  return SRG_OK;
+}
+
+// Stops recording, waits for the device, and accumulates per kernel kind: milliseconds, algorithmic FLOPs, launches.
+int srg_profile_end(int max_kinds, double* ms, double* flops, long long* launches) {
+  g_prof.enabled = false;
+  SRG_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < max_kinds; ++k) {
+    ms[k] = 0.0;
+    flops[k] = 0.0;
+    launches[k] = 0;
+  }
+  for (int i = 0; i < g_prof.n; ++i) {
+    float t = 0.f;
+    SRG_CUDA(cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]));
+    const int k = g_prof.kind[i];
+    if (k >= 0 && k < max_kinds) {
+      ms[k] += t;
+      flops[k] += g_prof.flops[i];
+      launches[k] += 1;
+    }
+  }
+  g_prof.n = 0;
+  return SRG_OK;
+}
+
+const char* srg_profile_kind_name(int kind) {
+  static const char* epi[] = {"store_bf16", "store_f32", "gru_zr", "gru_h", "logits", "bwd_drh", "?", "?"};
+  static thread_local char buf[64];
+  const int e = kind / 4;
+  snprintf(buf, sizeof(buf), "gemm_%s_%s%s", epi[e & 7], (kind & 2) ? "aT" : "a", (kind & 1) ? "bT" : "b");
+  return buf;
+}
+
 int srg_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* C, int64_t ldc,
                   int c_dtype, int M, int N, int K, const float* bias, float alpha, int cg, int k_splits, int reduce,
                   void* stream) {

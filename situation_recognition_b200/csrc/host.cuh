@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <string>
 #include "gemm.cuh"
 
@@ -46,6 +47,26 @@ enum : int {
     int _rc = (expr);            \
     if (_rc != 0) return _rc;    \
   } while (0)
+
+// ---------------------------------------------------------------- launch accounting / live kernel timing
+// g_launches counts every kernel this library launches (bench.py reports it as "gpu_launches").
+inline std::atomic<long long> g_launches{0};
+
+// Optional CUDA-event bracket around every GEMM launch, grouped by kernel kind, so that bench.py can report the
+// duration of the dominant kernel measured inside the timed region, on the launching stream.
+constexpr int kProfMaxRecords = 16384;
+constexpr int kProfKinds = 32;
+struct ProfState {
+  bool enabled = false;
+  int n = 0;
+  cudaEvent_t ev0[kProfMaxRecords];
+  cudaEvent_t ev1[kProfMaxRecords];
+  int created = 0;
+  int kind[kProfMaxRecords];
+  double flops[kProfMaxRecords];
+};
+inline ProfState g_prof;
+inline int prof_kind(int epi, bool a_mn, bool b_mn) { return epi * 4 + (a_mn ? 2 : 0) + (b_mn ? 1 : 0); }
 
 // ---------------------------------------------------------------- TMA descriptors
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -163,7 +184,21 @@ inline int launch_gemm_inst(const GemmProblem& p, const GemmMaps& maps, const Ge
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CG > 1) ? 1 : 0;
+  int rec = -1;
+  if (g_prof.enabled && g_prof.n < kProfMaxRecords) {
+    rec = g_prof.n++;
+    if (rec >= g_prof.created) {
+      SRG_CUDA(cudaEventCreate(&g_prof.ev0[rec]));
+      SRG_CUDA(cudaEventCreate(&g_prof.ev1[rec]));
+      g_prof.created = rec + 1;
+    }
+    g_prof.kind[rec] = prof_kind(EPI, A_MN, B_MN);
+    g_prof.flops[rec] = 2.0 * p.M * static_cast<double>(p.N) * args.total_kb * kBlockK;
+    SRG_CUDA(cudaEventRecord(g_prof.ev0[rec], stream));
+  }
   SRG_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, args));
+  if (rec >= 0) SRG_CUDA(cudaEventRecord(g_prof.ev1[rec], stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return SRG_OK;
 }
 

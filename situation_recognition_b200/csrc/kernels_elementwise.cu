@@ -460,6 +460,7 @@ __global__ void k_fill_f32(float* p, int64_t n, float v) {
 
 #define SRG_LAUNCH_CHECK()                                                                      \
   do {                                                                                          \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
     cudaError_t _e = cudaGetLastError();                                                        \
     if (_e != cudaSuccess)                                                                      \
       return set_error(SRG_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

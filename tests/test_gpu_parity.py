@@ -1,0 +1,260 @@
+"""-m gpu parity tests: the CUDA path (through the C-ABI, via the drop-in Python host) against
+  * the golden fixtures produced by the UNMODIFIED reference (tests/golden, oracle/make_golden.py), and
+  * the CPU oracle (oracle/ggnn_oracle.py) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): index/mask work bit-exact; fp32 mode max|d| / max|ref| <= 1e-4 and identical
+argmax on >= 99.9 % of rows; bf16 mode <= 2e-2.  Error metric: max absolute difference relative to the largest
+reference magnitude of the tensor (element-wise relative error is meaningless on near-zero logits).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import situation_recognition_b200 as S
+from oracle import ggnn_oracle as O
+from situation_recognition_b200.synthetic import make_batch, make_train_json
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FP32_TOL, BF16_TOL = 1e-4, 2e-2
+
+
+def relmax(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def agree(a, b):
+    return (a.detach().argmax(-1).cpu() == b.detach().argmax(-1).cpu()).float().mean().item()
+
+
+@pytest.fixture(scope="module")
+def enc_syn():
+    return S.imsitu_encoder(make_train_json(seed=0), verbose=False)
+
+
+@pytest.fixture(scope="module")
+def enc_over():
+    ann = json.loads(str(np.load(os.path.join(GOLDEN, "encoder_overfitting.npz"))["annotations_json"]))
+    return S.imsitu_encoder(ann, verbose=False)
+
+
+def golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+def model_from(params, enc, D, precision):
+    m = S.FCGGNN(enc, D, backbone=None, precision=precision)
+    res = m.load_state_dict({k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in params.items()},
+                            strict=False)
+    assert not res.unexpected_keys and not res.missing_keys
+    return m.cuda()
+
+
+def golden_params(g):
+    return {k[len("param."):]: v for k, v in g.items() if k.startswith("param.")}
+
+
+# ---------------------------------------------------------------------------------------------- K1: index / mask
+def test_gather_mask_bit_exact_all_verbs(enc_syn):
+    g = golden("encoder_synthetic504.npz")
+    m = S.FCGGNN(enc_syn, 256, backbone=None).cuda()
+    verbs = torch.arange(504, device="cuda")
+    role_idx, mask, bad = m.gather_mask(verbs)
+    assert role_idx.dtype == torch.int64 and mask.dtype == torch.float32
+    assert np.array_equal(role_idx.cpu().numpy(), g["role_ids_batch_all"])
+    assert np.array_equal(mask.cpu().numpy(), g["adj_all"])
+    assert int(bad.item()) == 0
+    rnd = torch.from_numpy(g["rand_verbs"]).cuda()
+    role_idx, mask, _ = m.gather_mask(rnd)
+    assert np.array_equal(role_idx.cpu().numpy(), g["rand_role_ids"])
+    assert np.array_equal(mask.cpu().numpy(), g["rand_adj"])
+    # same thing against the API-compatible encoder on a large random batch
+    big = torch.randint(0, 504, (6144,), generator=torch.Generator().manual_seed(1))
+    role_idx, mask, _ = m.gather_mask(big.cuda())
+    assert torch.equal(role_idx.cpu(), enc_syn.get_role_ids_batch(big))
+    assert torch.equal(mask.cpu(), enc_syn.get_adj_matrix_noself(big))
+
+
+def test_gather_mask_edge_cases(enc_syn, enc_over):
+    m = S.FCGGNN(enc_syn, 256, backbone=None).cuda()
+    role_idx, mask, _ = m.gather_mask(torch.zeros(0, dtype=torch.int64, device="cuda"))
+    assert role_idx.shape == (0, 6) and mask.shape == (0, 6, 6)
+    _, _, bad = m.gather_mask(torch.tensor([3, 504], device="cuda"))
+    assert int(bad.item()) == 1                                  # out-of-range verb id is flagged, not read
+    g = golden("encoder_overfitting.npz")                          # R = 4 vocabulary of the reference's own fixture
+    m4 = S.FCGGNN(enc_over, 256, backbone=None).cuda()
+    role_idx, mask, _ = m4.gather_mask(torch.arange(5, device="cuda"))
+    assert np.array_equal(role_idx.cpu().numpy(), g["role_ids_batch_all"])
+    assert np.array_equal(mask.cpu().numpy(), g["adj_all"])
+
+
+# ---------------------------------------------------------------------------------------------- golden (reference)
+@pytest.mark.parametrize("cta_group", [2, 1])
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_golden_forward(enc_over, precision, tol, cta_group):
+    g = golden("model_overfitting_D256.npz")
+    m = model_from(golden_params(g), enc_over, 256, precision).eval()
+    m._engine_for(torch.device("cuda", 0)).set_cta_group(cta_group)
+    with torch.no_grad():
+        h = m.ggsnn(torch.from_numpy(g["ggsnn_in_noun"]).cuda(), mask=torch.from_numpy(g["ggsnn_mask"]).cuda())
+        assert relmax(h, torch.from_numpy(g["ggsnn_out_noun"])) <= tol
+        h = m.ggsnn(torch.from_numpy(g["ggsnn_in_verb"]).cuda(), verb=True)
+        assert relmax(h, torch.from_numpy(g["ggsnn_out_verb"])) <= tol
+        feat, gt_verb = torch.from_numpy(g["feat"]).cuda(), torch.from_numpy(g["gt_verb"]).cuda()
+        gt_nouns = torch.from_numpy(g["gt_nouns"]).cuda()
+        pv, pn, gpn = m(feat, gt_verb)
+        assert pv.shape == (5, 5) and pn.shape == (5, 4, 30) and gpn.shape == (5, 4, 30)
+        for mine, key in ((pv, "pred_verb"), (pn, "pred_nouns"), (gpn, "gt_pred_nouns")):
+            ref = torch.from_numpy(g[key])
+            assert relmax(mine, ref) <= tol, key
+            if precision == "fp32":
+                assert agree(mine, ref) == 1.0, key
+        ltol = 1e-4 if precision == "fp32" else 2e-2
+        assert abs(m.verb_loss(pv, gt_verb).item() - float(g["verb_loss"])) <= ltol * float(g["verb_loss"])
+        assert abs(m.nouns_loss(pn, gt_nouns).item() - float(g["nouns_loss"])) <= ltol * float(g["nouns_loss"])
+        assert abs(m.nouns_loss(gpn, gt_nouns).item() - float(g["gt_nouns_loss"])) <= ltol * float(g["gt_nouns_loss"])
+
+
+def test_golden_gradients(enc_over):
+    """autograd of the unmodified reference (verb_loss + nouns_loss, sr.py:76) vs the CUDA backward (bf16 operands)."""
+    g = golden("model_overfitting_D256.npz")
+    m = model_from(golden_params(g), enc_over, 256, "bf16").eval()
+    feat, gt_verb = torch.from_numpy(g["feat"]).cuda(), torch.from_numpy(g["gt_verb"]).cuda()
+    gt_nouns = torch.from_numpy(g["gt_nouns"]).cuda()
+    pv, pn, gpn = m(feat, gt_verb)
+    assert torch.equal(pv.argmax(-1).cpu(), torch.from_numpy(g["pred_verb"]).argmax(-1))
+    (m.verb_loss(pv, gt_verb) + m.nouns_loss(pn, gt_nouns)).backward()
+    for k, p in m.named_parameters():
+        ref = torch.from_numpy(g["grad." + k])
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert relmax(got, ref) <= 3e-2, k
+    # the padding row of role_emb never receives a gradient (nn.Embedding padding_idx, model.py:95-97)
+    assert float(m.role_emb.weight.grad[enc_over.get_num_roles()].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------- oracle, real sizes
+@pytest.fixture(scope="module")
+def cfg2(enc_syn):
+    """BASELINE.json configs[1]: forward, batch 256, D=2048, 504/190/2001/6."""
+    B, D = 256, 2048
+    params = O.init_params(504, 190, 2001, D, seed=0)
+    fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=1234)
+    t, c = O.build_tables(enc_syn.roles_per_verb, enc_syn.verb_list, enc_syn.role_list)
+    with torch.no_grad():
+        pv, pn, gpn = O.forward(params, fv, fn, gt_verb, t, c)
+        losses = (O.verb_loss(pv, gt_verb), O.nouns_loss(pn, gt_nouns, 2001), O.nouns_loss(gpn, gt_nouns, 2001))
+    return dict(params=params, batch=(fv, fn, gt_verb, gt_nouns), out=(pv, pn, gpn), losses=losses, tables=(t, c))
+
+
+def test_config2_fp32_parity(enc_syn, cfg2):
+    m = model_from(cfg2["params"], enc_syn, 2048, "fp32").eval()
+    fv, fn, gt_verb, gt_nouns = [x.cuda() for x in cfg2["batch"]]
+    pv, pn, gpn = cfg2["out"]
+    with torch.no_grad():
+        mpv, mpn, mgpn = m(fv, gt_verb, img_nouns=fn)
+        assert mpn.shape == (256, 6, 2001) and mpv.shape == (256, 504)
+        assert relmax(mpv, pv) <= FP32_TOL
+        assert relmax(mgpn, gpn) <= FP32_TOL
+        assert agree(mpv, pv) >= 0.999
+        assert agree(mgpn, gpn) >= 0.999
+        same = (mpv.argmax(-1).cpu() == pv.argmax(-1))
+        assert same.float().mean().item() >= 0.999
+        assert relmax(mpn.cpu()[same], pn[same]) <= FP32_TOL       # pred-verb path, where the verbs agree
+        assert agree(mpn.cpu()[same], pn[same]) >= 0.999
+        vl, nl, gl = cfg2["losses"]
+        assert abs(m.verb_loss(mpv, gt_verb).item() - float(vl)) <= 1e-4 * float(vl)
+        assert abs(m.nouns_loss(mgpn, gt_nouns).item() - float(gl)) <= 1e-4 * float(gl)
+
+
+def test_config2_bf16_parity(enc_syn, cfg2):
+    m = model_from(cfg2["params"], enc_syn, 2048, "bf16").eval()
+    fv, fn, gt_verb, gt_nouns = [x.cuda() for x in cfg2["batch"]]
+    pv, pn, gpn = cfg2["out"]
+    with torch.no_grad():
+        mpv, mpn, mgpn = m(fv, gt_verb, img_nouns=fn)
+    assert relmax(mpv, pv) <= BF16_TOL and relmax(mgpn, gpn) <= BF16_TOL
+    # random-init logits are nearly tied (median top1-top2 gap ~1e-2 of max|logit|): bf16 operands flip ~1 % of the
+    # argmaxes against the fp32 oracle; the 99.9 % criterion is asserted in fp32 mode above.
+    assert agree(mgpn, gpn) >= 0.98 and agree(mpv, pv) >= 0.98
+
+
+def test_pad_rows_share_one_trajectory(enc_syn, cfg2):
+    """Size-independent property: pad nodes start at 0 and only see themselves, so within a
+    batch all pad rows of the gt-verb noun path carry identical logits."""
+    m = model_from(cfg2["params"], enc_syn, 2048, "bf16").eval()
+    fv, fn, gt_verb, _ = [x.cuda() for x in cfg2["batch"]]
+    with torch.no_grad():
+        gpn = m.predict_nouns(fn, gt_verb, 256)
+    counts = torch.tensor([enc_syn.get_role_count(int(v)) for v in gt_verb.cpu()])
+    pad = (torch.arange(6)[None, :] >= counts[:, None])
+    rows = gpn.cpu()[pad]
+    assert rows.shape[0] > 100
+    assert (rows - rows[0]).abs().max().item() == 0.0
+
+
+def test_images_are_independent_and_batch_one(enc_syn, cfg2):
+    """Ragged / tiny batches: B = 1 and B = 7 reproduce the corresponding rows of the B = 256 run bit for bit."""
+    m = model_from(cfg2["params"], enc_syn, 2048, "fp32").eval()
+    fv, fn, gt_verb, _ = [x.cuda() for x in cfg2["batch"]]
+    with torch.no_grad():
+        full = m.predict_nouns(fn, gt_verb, 256)
+        one = m.predict_nouns(fn[3:4], gt_verb[3:4], 1)
+        seven = m.predict_nouns(fn[100:107], gt_verb[100:107], 7)
+        vfull = m.predict_verb(fv, 256)
+        vone = m.predict_verb(fv[9:10], 1)
+    assert torch.equal(one[0], full[3]) and torch.equal(seven, full[100:107]) and torch.equal(vone[0], vfull[9])
+
+
+def test_train_step_gradients_vs_oracle(enc_syn):
+    B, D = 48, 2048
+    params = O.init_params(504, 190, 2001, D, seed=0)
+    fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=77)
+    t, c = O.build_tables(enc_syn.roles_per_verb, enc_syn.verb_list, enc_syn.role_list)
+    g = torch.Generator().manual_seed(5)
+    keeps = (torch.rand(B, D, generator=g) < 0.5, torch.rand(B * 6, D, generator=g) < 0.5,
+             torch.rand(B * 6, D, generator=g) < 0.5)
+    (vl, nl, gl), grads, (pv, pn, gpn) = O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, 2001, keeps, 0.5)
+    m = model_from(params, enc_syn, D, "bf16").train()
+    m.dropout_masks = tuple(k.to(torch.uint8).cuda() for k in keeps)
+    mpv, mpn, mgpn = m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())
+    lv, ln, lg = m.verb_loss(mpv, gt_verb.cuda()), m.nouns_loss(mpn, gt_nouns.cuda()), m.nouns_loss(mgpn, gt_nouns.cuda())
+    (lv + ln).backward()
+    assert relmax(mgpn, gpn) <= BF16_TOL and relmax(mpv, pv) <= BF16_TOL       # dropout-mask parity included
+    assert abs(lv.item() - float(vl)) <= 2e-3 * float(vl) and abs(lg.item() - float(gl)) <= 2e-3 * float(gl)
+    if torch.equal(mpv.argmax(-1).cpu(), pv.argmax(-1)):       # same predicted verbs => same pred-noun graph
+        assert abs(ln.item() - float(nl)) <= 2e-3 * float(nl)
+        for k, p in m.named_parameters():
+            assert relmax(p.grad, grads[k]) <= 3e-2, k
+
+
+def test_fp32_mode_is_forward_only(enc_syn):
+    m = S.FCGGNN(enc_syn, 256, backbone=None, precision="fp32").cuda()
+    x = torch.rand(4, 256, device="cuda")
+    with pytest.raises(S._lib.SrgError):
+        m(x, torch.zeros(4, dtype=torch.long, device="cuda"))
+
+
+def test_full_size_step_properties(enc_syn):
+    """BASELINE.json configs[2] size (B = 6144): determinism, finite outputs, and a 64-image sample of the batch
+    checked against the oracle (images are independent, so the oracle only needs the sampled rows)."""
+    B, D = 6144, 2048
+    params = O.init_params(504, 190, 2001, D, seed=0)
+    fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=1234)
+    m = model_from(params, enc_syn, D, "bf16").eval()
+    with torch.no_grad():
+        a = m.predict_nouns(fn.cuda(), gt_verb.cuda(), B)
+        b = m.predict_nouns(fn.cuda(), gt_verb.cuda(), B)
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    idx = torch.randperm(B, generator=torch.Generator().manual_seed(0))[:64]
+    t, c = O.build_tables(enc_syn.roles_per_verb, enc_syn.verb_list, enc_syn.role_list)
+    with torch.no_grad():
+        ref = O.predict_nouns(params, fn[idx], gt_verb[idx], t, c)
+    assert relmax(a.cpu()[idx], ref) <= BF16_TOL
+    # loss at full size against the closed form on the sample is not comparable; check the normalisation instead:
+    loss = m.nouns_loss(a, gt_nouns.cuda()).item()
+    assert 3 * np.log(2001) * 0.9 < loss < 3 * np.log(2001) * 1.1          # ~3*ln(2001) at random init
