@@ -218,7 +218,8 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
   const int num_n_tiles = args.N / BLOCK_N;
   const int k_splits = args.k_splits;
   const int kb_per_split = (args.total_kb + k_splits - 1) / k_splits;
-  const int total_work = num_m_tiles * num_n_tiles * k_splits;
+  const int tiles_mn = num_m_tiles * num_n_tiles;
+  const int total_work = tiles_mn * k_splits;
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -250,9 +251,9 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters) {
-        const int ks = w % k_splits;
-        const int nt = (w / k_splits) % num_n_tiles;
-        const int mt = w / (k_splits * num_n_tiles);
+        const int ks = w / tiles_mn;
+        const int nt = (w % tiles_mn) % num_n_tiles;
+        const int mt = (w % tiles_mn) / num_n_tiles;
         const int m0 = mt * kTileM * CG + static_cast<int>(cta_rank) * kTileM;
         const int nb0 = nt * BLOCK_N + static_cast<int>(cta_rank) * B_ROWS;
         const int kb_begin = ks * kb_per_split;
@@ -325,7 +326,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
       uint32_t phase = 0;
       int iter = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
-        const int ks = w % k_splits;
+        const int ks = w / tiles_mn;
         const int kb_begin = ks * kb_per_split;
         const int kb_end = min(args.total_kb, kb_begin + kb_per_split);
         const int acc = iter & 1;
@@ -364,8 +365,8 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
     (void)in_bar; (void)in_phase; (void)store_set;
 
     for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
-      const int nt = (w / k_splits) % num_n_tiles;
-      const int mt = w / (k_splits * num_n_tiles);
+      const int nt = (w % tiles_mn) % num_n_tiles;
+      const int mt = (w % tiles_mn) / num_n_tiles;
       const int row0 = mt * kTileM * CG + static_cast<int>(cta_rank) * kTileM + ew * 32;  // first row of this warp
       const int n0 = nt * BLOCK_N;
       const int acc = iter & 1;
