@@ -55,7 +55,7 @@ int srg_profile_end(int max_kinds, double* ms, double* flops, long long* launche
 }
 
 const char* srg_profile_kind_name(int kind) {
-  static const char* epi[] = {"store_bf16", "store_f32", "gru_zr", "gru_h", "logits", "bwd_drh", "?", "?"};
+  static const char* epi[] = {"store_bf16", "store_f32", "gru_zr", "gru_h", "logits", "bwd_drh", "bwd_dh", "?"};
   static thread_local char buf[64];
   const int e = kind / 4;
   snprintf(buf, sizeof(buf), "gemm_%s_%s%s", epi[e & 7], (kind & 2) ? "aT" : "a", (kind & 1) ? "bT" : "b");

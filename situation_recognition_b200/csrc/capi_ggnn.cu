@@ -30,7 +30,7 @@ struct srg_handle {
   int packed_prec = -1;
   int alloc_split = 0;  // K replication factor the buffers were allocated for (1 or 3)
   bf16 *Wp = nullptr, *Wzr = nullptr, *Wh = nullptr, *Wcn = nullptr, *Wcv = nullptr;
-  bf16 *Wm_stack = nullptr, *U_stack = nullptr, *Uh = nullptr;
+  bf16 *Wm_stack = nullptr, *UW_stack = nullptr, *Uh = nullptr;
   float *bp = nullptr, *bzr = nullptr, *bh = nullptr, *bcn = nullptr, *bcv = nullptr;
 };
 
@@ -54,7 +54,7 @@ struct PathBufs {
   float* mask = nullptr;
   // backward
   float *dh = nullptr, *dh_acc = nullptr, *da = nullptr;
-  bf16 *dpre_z = nullptr, *dpre_r = nullptr, *dpre_h = nullptr, *dm = nullptr, *dlb = nullptr;
+  bf16 *dpre_z[2] = {}, *dpre_h[2] = {}, *dpre_r = nullptr, *dm = nullptr, *adm = nullptr, *dlb = nullptr;
   size_t bytes = 0;
 };
 
@@ -122,10 +122,13 @@ PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* w
     pb.dh = bump.take<float>(MD);
     pb.dh_acc = bump.take<float>(MD);
     pb.da = bump.take<float>(MD);
-    pb.dpre_z = bump.take<bf16>(MD);
+    for (int i = 0; i < 2; ++i) {
+      pb.dpre_z[i] = bump.take<bf16>(MD);
+      pb.dpre_h[i] = bump.take<bf16>(MD);
+    }
     pb.dpre_r = bump.take<bf16>(MD);
-    pb.dpre_h = bump.take<bf16>(MD);
     pb.dm = bump.take<bf16>(MD);
+    pb.adm = (mode == SRG_MODE_NOUN) ? bump.take<bf16>(MD) : nullptr;
     pb.dlb = bump.take<bf16>(static_cast<size_t>(M) * npad);
   }
   pb.bytes = bump.off + 1024;
@@ -329,15 +332,19 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
     if (use_drop) SRG_TRY(launch_dropout_bwd(pb.da, keep, 1.0f / (1.0f - drop_p), MD, pb.dh, s));
   }
 
-  float* dh = pb.dh;
+  // dL/dh' of the last step comes from the classifier; from there on every step's "pre" work (GRU-gate derivatives of
+  // step t-1) is fused into the epilogue of the GEMM that completes dL/dh of step t (EPI_DH).
   float* dh_acc = pb.dh_acc;
+  int cur = 0;
+  SRG_TRY(launch_gru_bwd_pre(pb.dh, static_cast<const bf16*>(pb.st[T - 1].z), pb.st[T - 1].hc, pb.hb_hi[T - 1], MD,
+                             pb.dpre_z[cur], pb.dpre_h[cur], dh_acc, s));
   for (int t = T - 1; t >= 0; --t) {
     StepBufs& st = pb.st[t];
-    SRG_TRY(launch_gru_bwd_pre(dh, static_cast<const bf16*>(st.z), st.hc, pb.hb_hi[t], MD, pb.dpre_z, pb.dpre_h,
-                               dh_acc, s));
+    bf16* dpre_z = pb.dpre_z[cur];
+    bf16* dpre_h = pb.dpre_h[cur];
     {  // d(r*h) = dpre_h U_h ; fused: dpre_r = drh*h*r*(1-r), dh_acc += drh*r
       GemmProblem p = base_problem(h, M, D);
-      add_seg(p, pb.dpre_h, M, D, 0, D);
+      add_seg(p, dpre_h, M, D, 0, D);
       p.b_mn = true;
       p.b = mat(h->Uh, D, D, D, DT_BF16);
       p.epi = EPI_DRH;
@@ -349,8 +356,8 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
     }
     {  // dm = [dpre_h | dpre_z | dpre_r] [W_h ; W_z ; W_r]
       GemmProblem p = base_problem(h, M, D);
-      add_seg(p, pb.dpre_h, M, D, 0, D);
-      add_seg(p, pb.dpre_z, M, D, 0, D);
+      add_seg(p, dpre_h, M, D, 0, D);
+      add_seg(p, dpre_z, M, D, 0, D);
       add_seg(p, pb.dpre_r, M, D, 0, D);
       p.b_mn = true;
       p.b = mat(h->Wm_stack, 3 * D, D, D, DT_BF16);
@@ -358,51 +365,48 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
       p.io[0] = mat(pb.dm, M, D, D, DT_BF16);
       SRG_TRY(run_gemm(p, h->dev, s));
     }
-    {  // dh_acc += [dpre_z | dpre_r] [U_z ; U_r]
-      GemmProblem p = base_problem(h, M, D);
-      add_seg(p, pb.dpre_z, M, D, 0, D);
-      add_seg(p, pb.dpre_r, M, D, 0, D);
-      p.b_mn = true;
-      p.b = mat(h->U_stack, 2 * D, D, D, DT_BF16);
-      p.epi = EPI_STORE_F32;
-      p.flags = FLAG_REDUCE;
-      p.io[0] = mat(dh_acc, M, D, D, DT_F32);
-      SRG_TRY(run_gemm(p, h->dev, s));
+    // the aggregation is linear and commutes with W_p: push dm through its transpose first (noun mode)
+    const bf16* adm = pb.dm;
+    if (mode == SRG_MODE_NOUN) {
+      SRG_TRY(launch_aggregate_t_bf16(pb.dm, pb.mask, B, R, D, pb.adm, s));
+      adm = pb.adm;
     }
-    {  // da = dm W_p, then through the aggregation (noun) or straight into dh (verb)
+    {  // dL/dh_t = dh_acc + [dpre_z | dpre_r | adm] [U_z ; U_r ; W_p], then the gate derivatives of step t-1
       GemmProblem p = base_problem(h, M, D);
-      add_seg(p, pb.dm, M, D, 0, D);
+      add_seg(p, dpre_z, M, D, 0, D);
+      add_seg(p, pb.dpre_r, M, D, 0, D);
+      add_seg(p, adm, M, D, 0, D);
       p.b_mn = true;
-      p.b = mat(h->Wp, D, D, D, DT_BF16);
-      p.epi = EPI_STORE_F32;
-      if (mode == SRG_MODE_NOUN) {
-        p.io[0] = mat(pb.da, M, D, D, DT_F32);
-        SRG_TRY(run_gemm(p, h->dev, s));
-        SRG_TRY(launch_aggregate_bwd(dh_acc, pb.da, pb.mask, B, R, D, dh, s));
-      } else {
-        p.flags = FLAG_REDUCE;
-        p.io[0] = mat(dh_acc, M, D, D, DT_F32);
-        SRG_TRY(run_gemm(p, h->dev, s));
-        float* tmp = dh;
-        dh = dh_acc;
-        dh_acc = tmp;
+      p.b = mat(h->UW_stack, 3 * D, D, D, DT_BF16);
+      p.epi = EPI_DH;
+      p.io[0] = mat(dh_acc, M, D, D, DT_F32);
+      if (t > 0) {
+        p.flags = FLAG_NEXT;
+        p.io[1] = mat(pb.st[t - 1].z, M, D, D, DT_BF16);
+        p.io[2] = mat(pb.st[t - 1].hc, M, D, D, DT_BF16);
+        p.io[3] = mat(pb.hb_hi[t - 1], M, D, D, DT_BF16);
+        p.io[4] = mat(pb.dpre_z[cur ^ 1], M, D, D, DT_BF16);
+        p.io[5] = mat(pb.dpre_h[cur ^ 1], M, D, D, DT_BF16);
       }
+      SRG_TRY(run_gemm(p, h->dev, s));
     }
     // ---- weight gradients of this step (the 7 linears are shared by all steps and both paths: accumulate)
     const bf16* msg_in = (mode == SRG_MODE_NOUN) ? st.a_hi : pb.hb_hi[t];
     SRG_TRY(wgrad(h, pb.dm, D, D, msg_in, D, M, g->W_p, s));
-    SRG_TRY(wgrad(h, pb.dpre_z, D, D, st.m_hi, D, M, g->W_z, s));
-    SRG_TRY(wgrad(h, pb.dpre_z, D, D, pb.hb_hi[t], D, M, g->U_z, s));
+    SRG_TRY(wgrad(h, dpre_z, D, D, st.m_hi, D, M, g->W_z, s));
+    SRG_TRY(wgrad(h, dpre_z, D, D, pb.hb_hi[t], D, M, g->U_z, s));
     SRG_TRY(wgrad(h, pb.dpre_r, D, D, st.m_hi, D, M, g->W_r, s));
     SRG_TRY(wgrad(h, pb.dpre_r, D, D, pb.hb_hi[t], D, M, g->U_r, s));
-    SRG_TRY(wgrad(h, pb.dpre_h, D, D, st.m_hi, D, M, g->W_h, s));
-    SRG_TRY(wgrad(h, pb.dpre_h, D, D, st.rh_hi, D, M, g->U_h, s));
-    SRG_TRY(launch_colsum(pb.dpre_z, D, M, D, g->b_Wz, 1.f, g->b_Uz, 1.f, s));
-    SRG_TRY(launch_colsum(pb.dpre_r, D, M, D, g->b_Wr, 1.f, g->b_Ur, 1.f, s));
-    SRG_TRY(launch_colsum(pb.dpre_h, D, M, D, g->b_Wh, 1.f, g->b_Uh, 1.f, s));
-    SRG_TRY(launch_colsum(pb.dm, D, M, D, g->b_p, (mode == SRG_MODE_NOUN) ? static_cast<float>(R) : 1.f, nullptr, 0.f,
-                          s));
+    SRG_TRY(wgrad(h, dpre_h, D, D, st.m_hi, D, M, g->W_h, s));
+    SRG_TRY(wgrad(h, dpre_h, D, D, st.rh_hi, D, M, g->U_h, s));
+    ColsumJob jobs[4] = {{dpre_z, g->b_Wz, g->b_Uz, 1.f},
+                         {pb.dpre_r, g->b_Wr, g->b_Ur, 1.f},
+                         {dpre_h, g->b_Wh, g->b_Uh, 1.f},
+                         {pb.dm, g->b_p, nullptr, (mode == SRG_MODE_NOUN) ? static_cast<float>(R) : 1.f}};
+    SRG_TRY(launch_colsum_multi(jobs, 4, D, M, D, s));
+    cur ^= 1;
   }
+  float* dh = dh_acc;
   pb.dh = dh;  // gradient w.r.t. the initial node states
   return SRG_OK;
 }
@@ -423,7 +427,7 @@ int ensure_pack_buffers(srg_handle* h, int split) {
   SRG_TRY(re(&h->Wcv, static_cast<size_t>(h->Vpad) * D * split));
   if (!h->Wm_stack) {
     SRG_TRY(re(&h->Wm_stack, 3 * D * D));
-    SRG_TRY(re(&h->U_stack, 2 * D * D));
+    SRG_TRY(re(&h->UW_stack, 3 * D * D));
     SRG_TRY(re(&h->Uh, D * D));
     SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->bp), D * sizeof(float)));
     SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->bzr), 2 * D * sizeof(float)));
@@ -471,7 +475,7 @@ int srg_create(srg_handle** out, int device, int D, int R, int T, int n_verbs, i
 int srg_destroy(srg_handle* h) {
   if (!h) return SRG_OK;
   void* ptrs[] = {h->d_verb2roles, h->d_role_count, h->d_bad, h->Wp, h->Wzr, h->Wh, h->Wcn, h->Wcv, h->Wm_stack,
-                  h->U_stack, h->Uh, h->bp, h->bzr, h->bh, h->bcn, h->bcv};
+                  h->UW_stack, h->Uh, h->bp, h->bzr, h->bh, h->bcn, h->bcv};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete h;
@@ -544,8 +548,9 @@ int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* st
     SRG_TRY(launch_pack_weight(p->W_h, D, D, D, h->Wm_stack, D, 0, 0, s));
     SRG_TRY(launch_pack_weight(p->W_z, D, D, D, h->Wm_stack + static_cast<size_t>(D) * D, D, 0, 0, s));
     SRG_TRY(launch_pack_weight(p->W_r, D, D, D, h->Wm_stack + 2 * static_cast<size_t>(D) * D, D, 0, 0, s));
-    SRG_TRY(launch_pack_weight(p->U_z, D, D, D, h->U_stack, D, 0, 0, s));
-    SRG_TRY(launch_pack_weight(p->U_r, D, D, D, h->U_stack + static_cast<size_t>(D) * D, D, 0, 0, s));
+    SRG_TRY(launch_pack_weight(p->U_z, D, D, D, h->UW_stack, D, 0, 0, s));
+    SRG_TRY(launch_pack_weight(p->U_r, D, D, D, h->UW_stack + static_cast<size_t>(D) * D, D, 0, 0, s));
+    SRG_TRY(launch_pack_weight(p->W_p, D, D, D, h->UW_stack + 2 * static_cast<size_t>(D) * D, D, 0, 0, s));
     SRG_TRY(launch_pack_weight(p->U_h, D, D, D, h->Uh, D, 0, 0, s));
   }
   SRG_TRY(launch_pack_bias(p->b_p, nullptr, D, D, h->bp, s));

@@ -61,6 +61,17 @@ int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, c
                          const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_roles, int B,
                          int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s);
 
+// adm[b,j,:] = sum_i mask[b,i,j] * dm[b,i,:]   (bf16 in / bf16 out; the aggregation commutes with the W_p GEMM)
+int launch_aggregate_t_bf16(const bf16* dm, const float* mask, int B, int R, int D, bf16* adm, cudaStream_t s);
+// up to 4 column sums in one launch
+struct ColsumJob {
+  const bf16* X;
+  float* out1;
+  float* out2;
+  float scale;
+};
+int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows, int n_cols, cudaStream_t s);
+
 int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s);
 
 }  // namespace srg

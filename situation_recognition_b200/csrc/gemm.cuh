@@ -36,9 +36,10 @@ enum EpiKind : int {
   EPI_H = 3,           // GRU candidate + state update: hc = tanh(.), h' = h + z*(hc - h)
   EPI_LOGITS = 4,      // classifier: logits + per-tile row softmax statistics
   EPI_DRH = 5,         // backward: drh = acc; dpre_r = drh*h*r*(1-r); dh_acc += drh*r
+  EPI_DH = 6,          // backward: g = acc + dh_acc = dL/dh_{t-1}'; fused GRU-gate derivatives of step t-1
 };
 
-enum : int { FLAG_LO = 1, FLAG_STASH = 2, FLAG_REDUCE = 4 };
+enum : int { FLAG_LO = 1, FLAG_STASH = 2, FLAG_REDUCE = 4, FLAG_NEXT = 8 };
 
 struct GemmMaps {
   CUtensorMap a[kMaxAMaps];
@@ -70,6 +71,7 @@ struct EpiTraits {
                                 : (EPI == EPI_ZR)        ? (F32 ? 6 : 5)
                                 : (EPI == EPI_H)         ? (F32 ? 6 : 4)
                                 : (EPI == EPI_LOGITS)    ? 4
+                                : (EPI == EPI_DH)        ? 5
                                                          : 6;
 };
 
@@ -655,6 +657,67 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
               ptx::tma_store_2d(&maps.io[2], slot_ptr(S_DP), gcol, row0);
               ptx::tma_store_2d(&maps.io[3], slot_ptr(S_DH), gcol, row0);
               ptx::tma_store_2d(&maps.io[3], slot_ptr(S_DH + 1), gcol + 32, row0);
+            }
+            ptx::tma_commit_group();
+          }
+        } else if constexpr (EPI == EPI_DH) {
+          // g = acc + dh_acc is the gradient w.r.t. the state entering this step = the output of step t-1.
+          //   io0 = dh_acc fp32 (read-modify-write in place)
+          // FLAG_NEXT (t > 0): also apply the GRU update derivative of step t-1 in the same pass:
+          //   io1 = z, io2 = hc, io3 = h (bf16, step t-1);  io4 = dpre_z out, io5 = dpre_h out (bf16)
+          //   dpre_z = g*(hc-h)*z*(1-z), dpre_h = g*z*(1-hc^2), dh_acc = g*(1-z)
+          constexpr int S_DH = 0, S_Z = 2, S_HC = 3, S_H = 4;
+          const bool next = (args.flags & FLAG_NEXT) != 0;
+          if (lane == 0) {
+            ptx::tma_wait_group_read<0>();
+            ptx::mbar_arrive_expect_tx(in_bar, (next ? 5 : 2) * kSlotBytes);
+            ptx::tma_load_2d(&maps.io[0], in_bar, slot_ptr(S_DH), gcol, row0);
+            ptx::tma_load_2d(&maps.io[0], in_bar, slot_ptr(S_DH + 1), gcol + 32, row0);
+            if (next) {
+              ptx::tma_load_2d(&maps.io[1], in_bar, slot_ptr(S_Z), gcol, row0);
+              ptx::tma_load_2d(&maps.io[2], in_bar, slot_ptr(S_HC), gcol, row0);
+              ptx::tma_load_2d(&maps.io[3], in_bar, slot_ptr(S_H), gcol, row0);
+            }
+          }
+          ptx::mbar_wait(in_bar, in_phase);
+          in_phase ^= 1u;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            ptx::tmem_ld_32x32(tacc + cc * 64 + half * 32, accv);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float dh[8];
+              slot_ld_f32x8(slot(S_DH + half), lane, g, dh);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dh[i] += accv[g * 8 + i];
+              if (next) {
+                float z[8], hc[8], h[8], dz[8], dc[8];
+                slot_ld_bf16x8(slot(S_Z), lane, half * 4 + g, z);
+                slot_ld_bf16x8(slot(S_HC), lane, half * 4 + g, hc);
+                slot_ld_bf16x8(slot(S_H), lane, half * 4 + g, h);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  dz[i] = dh[i] * (hc[i] - h[i]) * z[i] * (1.0f - z[i]);
+                  dc[i] = dh[i] * z[i] * (1.0f - hc[i] * hc[i]);
+                  dh[i] = dh[i] * (1.0f - z[i]);
+                }
+                slot_st_bf16x8(slot(S_Z), lane, half * 4 + g, dz);
+                slot_st_bf16x8(slot(S_HC), lane, half * 4 + g, dc);
+              }
+              slot_st_f32x8(slot(S_DH + half), lane, g, dh);
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (warp_active) {
+              ptx::tma_store_2d(&maps.io[0], slot_ptr(S_DH), gcol, row0);
+              ptx::tma_store_2d(&maps.io[0], slot_ptr(S_DH + 1), gcol + 32, row0);
+              if (next) {
+                ptx::tma_store_2d(&maps.io[4], slot_ptr(S_Z), gcol, row0);
+                ptx::tma_store_2d(&maps.io[5], slot_ptr(S_HC), gcol, row0);
+              }
             }
             ptx::tma_commit_group();
           }

@@ -221,6 +221,7 @@ inline int dispatch_gemm(const GemmProblem& p, const GemmMaps& maps, const GemmA
   SRG_CASE(false, true, EPI_STORE_BF16, false)
   SRG_CASE(false, true, EPI_STORE_F32, false)
   SRG_CASE(false, true, EPI_DRH, false)
+  SRG_CASE(false, true, EPI_DH, false)
   SRG_CASE(true, true, EPI_STORE_F32, false)
 #undef SRG_CASE
   return set_error(SRG_ERR_UNSUPPORTED, "no gemm kernel for a_mn=%d b_mn=%d epi=%d f32=%d", (int)p.a_mn, (int)p.b_mn,

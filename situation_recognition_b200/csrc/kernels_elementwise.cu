@@ -452,6 +452,95 @@ __global__ void k_node_init_bwd(const float* __restrict__ dh0, const bf16* __res
   }
 }
 
+__global__ void k_aggregate_t_bf16(const bf16* __restrict__ dm, const float* __restrict__ mask, int B, int R, int D,
+                                   bf16* __restrict__ adm) {
+  const int D8 = D / 8;
+  const int64_t total = static_cast<int64_t>(B) * D8;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(t / D8);
+    const int d = static_cast<int>(t % D8) * 8;
+    float g[kMaxR][8];
+#pragma unroll
+    for (int i = 0; i < kMaxR; ++i) {
+      if (i < R) {
+        const uint4 u = *reinterpret_cast<const uint4*>(dm + (static_cast<int64_t>(b) * R + i) * D + d);
+        g[i][0] = bf16_lo_f(u.x); g[i][1] = bf16_hi_f(u.x); g[i][2] = bf16_lo_f(u.y); g[i][3] = bf16_hi_f(u.y);
+        g[i][4] = bf16_lo_f(u.z); g[i][5] = bf16_hi_f(u.z); g[i][6] = bf16_lo_f(u.w); g[i][7] = bf16_hi_f(u.w);
+      }
+    }
+    const float* mb = mask + static_cast<int64_t>(b) * R * R;
+#pragma unroll
+    for (int j = 0; j < kMaxR; ++j) {
+      if (j < R) {
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < kMaxR; ++i) {
+          if (i < R) {
+            const float m = __ldg(mb + i * R + j);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fmaf(m, g[i][k], a[k]);
+          }
+        }
+        uint4 o;
+        const uint2 lo = pack4_bf16(a[0], a[1], a[2], a[3]), hi = pack4_bf16(a[4], a[5], a[6], a[7]);
+        o.x = lo.x; o.y = lo.y; o.z = hi.x; o.w = hi.y;
+        *reinterpret_cast<uint4*>(adm + (static_cast<int64_t>(b) * R + j) * D + d) = o;
+      }
+    }
+  }
+}
+
+struct ColsumJobs {
+  ColsumJob j[4];
+};
+// grid = (column chunks of 64, row slabs, jobs)
+__global__ void k_colsum_multi(ColsumJobs jobs, int64_t ld, int rows, int n_cols) {
+  __shared__ float2 red[8][32];
+  const ColsumJob job = jobs.j[blockIdx.z];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + lane * 2;
+  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float2 acc = make_float2(0.f, 0.f);
+  if (c < n_cols) {
+    int r = r0 + w;
+    for (; r + 24 < r1; r += 32) {   // 4 independent loads in flight per thread
+      const __nv_bfloat162 v0 = *reinterpret_cast<const __nv_bfloat162*>(job.X + static_cast<int64_t>(r) * ld + c);
+      const __nv_bfloat162 v1 = *reinterpret_cast<const __nv_bfloat162*>(job.X + static_cast<int64_t>(r + 8) * ld + c);
+      const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(job.X + static_cast<int64_t>(r + 16) * ld + c);
+      const __nv_bfloat162 v3 = *reinterpret_cast<const __nv_bfloat162*>(job.X + static_cast<int64_t>(r + 24) * ld + c);
+      const float2 f0 = __bfloat1622float2(v0), f1 = __bfloat1622float2(v1), f2 = __bfloat1622float2(v2),
+                   f3 = __bfloat1622float2(v3);
+      acc.x += (f0.x + f1.x) + (f2.x + f3.x);
+      acc.y += (f0.y + f1.y) + (f2.y + f3.y);
+    }
+    for (; r < r1; r += 8) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(job.X + static_cast<int64_t>(r) * ld + c));
+      acc.x += f.x;
+      acc.y += f.y;
+    }
+  }
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && c < n_cols) {
+    float2 t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      t.x += red[i][lane].x;
+      t.y += red[i][lane].y;
+    }
+    if (job.out1 != nullptr) {
+      atomicAdd(job.out1 + c, t.x * job.scale);
+      if (c + 1 < n_cols) atomicAdd(job.out1 + c + 1, t.y * job.scale);
+    }
+    if (job.out2 != nullptr) {
+      atomicAdd(job.out2 + c, t.x * job.scale);
+      if (c + 1 < n_cols) atomicAdd(job.out2 + c + 1, t.y * job.scale);
+    }
+  }
+}
+
 __global__ void k_fill_f32(float* p, int64_t n, float v) {
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -614,6 +703,27 @@ int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, c
   if (B <= 0) return SRG_OK;
   k_node_init_bwd<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(
       dh0, h0b, feat, role_emb, verb_emb, verb, verb2roles, n_roles, B, R, D, d_role_emb, d_verb_emb);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_aggregate_t_bf16(const bf16* dm, const float* mask, int B, int R, int D, bf16* adm, cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
+  k_aggregate_t_bf16<<<grid_for(static_cast<int64_t>(B) * D / 8), kThreads, 0, s>>>(dm, mask, B, R, D, adm);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows, int n_cols, cudaStream_t s) {
+  if (rows <= 0 || n_cols <= 0 || n_jobs <= 0) return SRG_OK;
+  if (n_jobs > 4) return set_error(SRG_ERR_ARG, "colsum_multi: at most 4 jobs");
+  ColsumJobs js;
+  for (int i = 0; i < 4; ++i) js.j[i] = jobs[i < n_jobs ? i : 0];
+  int slabs = (rows + 511) / 512;
+  if (slabs > 37) slabs = 37;
+  dim3 grid((n_cols + 63) / 64, slabs, n_jobs);
+  k_colsum_multi<<<grid, kThreads, 0, s>>>(js, ld, rows, n_cols);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }

@@ -258,3 +258,36 @@ def test_full_size_step_properties(enc_syn):
     # loss at full size against the closed form on the sample is not comparable; check the normalisation instead:
     loss = m.nouns_loss(a, gt_nouns.cuda()).item()
     assert 3 * np.log(2001) * 0.9 < loss < 3 * np.log(2001) * 1.1          # ~3*ln(2001) at random init
+
+
+def test_graphed_step_matches_eager(enc_syn):
+    """The CUDA-graph replay of a training step produces the same losses and parameter updates as eager launches."""
+    from situation_recognition_b200 import parallel
+    from situation_recognition_b200.graph import GraphedTrainStep
+    B, D = 24, 2048
+    params = O.init_params(504, 190, 2001, D, seed=0)
+    batch = [x.cuda() for x in make_batch(enc_syn, B, D, seed=9)]
+    g = torch.Generator().manual_seed(5)
+    keeps = tuple((torch.rand(r, D, generator=g) < 0.5).to(torch.uint8).cuda() for r in (B, B * 6, B * 6))
+    results = []
+    for graphed in (False, True):
+        m = model_from(params, enc_syn, D, "bf16").train()
+        m.dropout_masks = keeps
+        flat = parallel.attach(m)
+        opt = torch.optim.Adamax(m.parameters(), lr=0.002, capturable=True)
+        gs = GraphedTrainStep(m, opt, flat, B, warmup=0 if not graphed else 2)
+        if graphed:
+            snap = {k: v.detach().clone() for k, v in m.state_dict().items()}
+            gs.capture(batch)                       # warm-up steps move the weights: restore them, reset Adamax
+            m.load_state_dict(snap)
+            opt.state.clear()
+            opt2 = None
+            losses = [gs(*batch).clone() for _ in range(2)]
+        else:
+            for dst, src in zip(gs.static_in, batch):
+                dst.copy_(src)
+            losses = [gs._body().clone() for _ in range(2)]
+        torch.cuda.synchronize()
+        results.append((torch.stack(losses).cpu(), {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
+    (l0, p0), (l1, p1) = results
+    assert torch.allclose(l0[0], l1[0], rtol=1e-5, atol=1e-6)          # first step: identical weights and masks
