@@ -134,6 +134,40 @@ def main():
     case_b = run_model_case(ref_model, enc_syn, D=64, B=8, seed=12, train_json=train)
     # keep this fixture small: drop the big classifier gradient/param duplicates that case A already pins
     np.savez_compressed(os.path.join(OUT, "model_synthetic504_D64.npz"), **case_b)
+    # (4) the reference scorer (utils/imsitu_scorer.py) on seeded random logits with planted hits
+    from utils import imsitu_scorer as ref_scorer
+    g = torch.Generator().manual_seed(21)
+    B, V, R, L = 64, 504, 6, 200        # the scorer only ranks the last axis; 200 labels keep the fixture small
+    verbs = torch.randint(0, V, (B,), generator=g)
+    gt_nouns = torch.full((B, 3, R), L, dtype=torch.int64)
+    for b in range(B):
+        n = enc_syn.get_role_count(int(verbs[b]))
+        gt_nouns[b, :, :n] = torch.randint(0, L, (3, n), generator=g)
+    pred_verbs = torch.randn(B, V, generator=g)
+    pred_nouns = torch.randn(B, R, L, generator=g)
+    gt_pred_nouns = torch.randn(B, R, L, generator=g)
+    for b in range(B):          # plant correct answers so that every metric is exercised
+        if b % 3 == 0:
+            pred_verbs[b, verbs[b]] += 10
+        n = enc_syn.get_role_count(int(verbs[b]))
+        for r in range(n):
+            if (b + r) % 2 == 0 and b % 5 != 0:
+                pred_nouns[b, r, gt_nouns[b, (b + r) % 3, r]] += 10
+            if (b + r) % 4 != 1 and b % 7 != 0:
+                gt_pred_nouns[b, r, gt_nouns[b, r % 3, r]] += 10
+    sc = {"verbs": verbs.numpy(), "gt_nouns": gt_nouns.numpy(), "pred_verbs": pred_verbs.numpy(),
+          "pred_nouns": pred_nouns.numpy().astype(np.float16), "gt_pred_nouns": gt_pred_nouns.numpy().astype(np.float16)}
+    pn16, gpn16 = torch.from_numpy(sc["pred_nouns"]).float(), torch.from_numpy(sc["gt_pred_nouns"]).float()
+    for k in (1, 5):
+        s = ref_scorer.imsitu_scorer(enc_syn, k, 3)
+        s.add_point_both(pred_verbs[:40], verbs[:40], pn16[:40], gt_nouns[:40], gpn16[:40])
+        s.add_point_both(pred_verbs[40:], verbs[40:], pn16[40:], gt_nouns[40:], gpn16[40:])
+        avg = s.get_average_results_both()
+        keys = sorted(avg)
+        sc["top%d_keys" % k] = np.array(keys)
+        sc["top%d_avg" % k] = np.array([avg[x] for x in keys], dtype=np.float64)
+        sc["top%d_cards" % k] = np.array([[float(c[x]) for x in keys] for c in s.score_cards], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "scorer_synthetic504.npz"), **sc)
     for n in sorted(os.listdir(OUT)):
         print(n, os.path.getsize(os.path.join(OUT, n)))
 
