@@ -130,6 +130,8 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     steps, warmup = args.steps, args.warmup
     O, enc, params, batch, tables = oracle_setup(8)
     t0 = time.time()
@@ -174,6 +176,11 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the bench prints exactly one line on stdout: keep NCCL's own banner ("NCCL version ...") off it
+        if "SRG_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["SRG_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -184,7 +191,8 @@ def run_ours(args):
     if args.cta_group:
         model._engine_for(dev).set_cta_group(args.cta_group)
     flat = parallel.attach(model)
-    use_graph = not args.no_graph
+    # CUDA-graph replay on one GPU; with NCCL in the step the kernels are launched eagerly (--graph forces capture)
+    use_graph = (not args.no_graph) and (world == 1 or args.graph)
     opt = torch.optim.Adamax(model.parameters(), lr=0.002, capturable=use_graph)      # sr.py:472-473
     params = [p for p in model.parameters() if p.requires_grad]
 
@@ -315,7 +323,12 @@ def run_ours(args):
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without running NCCL / CUDA-graph destructors: a captured or in-flight communicator has been seen to
+        # block interpreter shutdown after the result line was already printed
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -327,6 +340,7 @@ def main():
     ap.add_argument("--batch", type=int, default=6144, help="global batch (BASELINE.json: 6144)")
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="capture the step into a CUDA graph even when N > 1")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

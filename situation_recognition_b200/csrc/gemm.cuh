@@ -27,7 +27,7 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kSlotBytes = 4096;  // 32 rows x 128 B
 constexpr int kMaxSeg = 8;
 constexpr int kMaxAMaps = 4;
-constexpr int kMaxIoMaps = 6;
+constexpr int kMaxIoMaps = 7;
 
 enum EpiKind : int {
   EPI_STORE_BF16 = 0,  // io0 = out hi (bf16), io1 = out lo (bf16, FLAG_LO)
@@ -39,7 +39,7 @@ enum EpiKind : int {
   EPI_DH = 6,          // backward: g = acc + dh_acc = dL/dh_{t-1}'; fused GRU-gate derivatives of step t-1
 };
 
-enum : int { FLAG_LO = 1, FLAG_STASH = 2, FLAG_REDUCE = 4, FLAG_NEXT = 8 };
+enum : int { FLAG_LO = 1, FLAG_STASH = 2, FLAG_REDUCE = 4, FLAG_NEXT = 8, FLAG_ADD = 16 };
 
 struct GemmMaps {
   CUtensorMap a[kMaxAMaps];
@@ -71,7 +71,7 @@ struct EpiTraits {
                                 : (EPI == EPI_ZR)        ? (F32 ? 6 : 5)
                                 : (EPI == EPI_H)         ? (F32 ? 6 : 4)
                                 : (EPI == EPI_LOGITS)    ? 4
-                                : (EPI == EPI_DH)        ? 5
+                                : (EPI == EPI_DH)        ? 6
                                                          : 6;
 };
 
@@ -666,13 +666,16 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
           // FLAG_NEXT (t > 0): also apply the GRU update derivative of step t-1 in the same pass:
           //   io1 = z, io2 = hc, io3 = h (bf16, step t-1);  io4 = dpre_z out, io5 = dpre_h out (bf16)
           //   dpre_z = g*(hc-h)*z*(1-z), dpre_h = g*z*(1-hc^2), dh_acc = g*(1-z)
-          constexpr int S_DH = 0, S_Z = 2, S_HC = 3, S_H = 4;
+          // FLAG_ADD: io6 = extra bf16 addend (the aggregated message gradient): g += add
+          constexpr int S_DH = 0, S_Z = 2, S_HC = 3, S_H = 4, S_ADD = 5;
           const bool next = (args.flags & FLAG_NEXT) != 0;
+          const bool has_add = (args.flags & FLAG_ADD) != 0;
           if (lane == 0) {
             ptx::tma_wait_group_read<0>();
-            ptx::mbar_arrive_expect_tx(in_bar, (next ? 5 : 2) * kSlotBytes);
+            ptx::mbar_arrive_expect_tx(in_bar, (2 + (next ? 3 : 0) + (has_add ? 1 : 0)) * kSlotBytes);
             ptx::tma_load_2d(&maps.io[0], in_bar, slot_ptr(S_DH), gcol, row0);
             ptx::tma_load_2d(&maps.io[0], in_bar, slot_ptr(S_DH + 1), gcol + 32, row0);
+            if (has_add) ptx::tma_load_2d(&maps.io[6], in_bar, slot_ptr(S_ADD), gcol, row0);
             if (next) {
               ptx::tma_load_2d(&maps.io[1], in_bar, slot_ptr(S_Z), gcol, row0);
               ptx::tma_load_2d(&maps.io[2], in_bar, slot_ptr(S_HC), gcol, row0);
@@ -691,6 +694,12 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
               slot_ld_f32x8(slot(S_DH + half), lane, g, dh);
 #pragma unroll
               for (int i = 0; i < 8; ++i) dh[i] += accv[g * 8 + i];
+              if (has_add) {
+                float ad[8];
+                slot_ld_bf16x8(slot(S_ADD), lane, half * 4 + g, ad);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dh[i] += ad[i];
+              }
               if (next) {
                 float z[8], hc[8], h[8], dz[8], dc[8];
                 slot_ld_bf16x8(slot(S_Z), lane, half * 4 + g, z);

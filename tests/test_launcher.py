@@ -1,0 +1,84 @@
+"""sr.py-compatible launcher: CLI surface on CPU; all five modes end to end on the GPU with a tiny synthetic dataset."""
+import json
+import os
+import re
+
+import pytest
+import torch
+
+
+def test_cli_flags_match_reference():
+    from situation_recognition_b200.sr import build_parser
+    flags = {a.option_strings[0] for a in build_parser()._actions if a.option_strings}
+    reference = {'--resume_model', '--evaluate_dev', '--evaluate_test', '--test_img', '--verb', '--subset',
+                 '--model_saving_name', '--saving_folder', '--imgset_dir', '--dataset_folder', '--train_file',
+                 '--dev_file', '--test_file', '--batch_size', '--num_workers', '--epochs', '--lr'}     # sr.py:384-420
+    assert reference <= flags
+    d = build_parser().parse_args([])
+    assert (d.batch_size, d.num_workers, d.epochs, d.lr) == (6144, 10, 1000, 0.002)
+
+
+def test_sharded_batch_sampler_covers_every_sample_once():
+    from situation_recognition_b200.imsitu_loader import ShardedBatchSampler
+    for n, gb, world in ((10, 4, 2), (7, 7, 1), (25, 8, 4), (5, 4, 4)):
+        per_rank = [list(ShardedBatchSampler(n, gb, r, world, shuffle=True, seed=3)) for r in range(world)]
+        assert len({len(x) for x in per_rank}) == 1                      # same number of steps on every rank
+        seen = sorted(i for x in per_rank for b in x for i in b)
+        assert set(seen) == set(range(n)) and len(seen) >= n
+
+
+def test_format_dict_matches_reference_format():
+    from situation_recognition_b200.utils import format_dict
+    assert format_dict({'verb': 0.3237, 'value': 0.7468}, '{:.2f}', '1-') == '1-verb: 32.37, 1-value: 74.68'
+
+
+def _make_dataset(root):
+    from PIL import Image
+    from situation_recognition_b200.synthetic import make_train_json
+    ann = make_train_json(seed=0, images_per_verb=1)
+    keys = list(ann)
+    train = {k: ann[k] for k in keys}
+    small = {k: ann[k] for k in keys[:6]}
+    os.makedirs(os.path.join(root, "imSitu"))
+    os.makedirs(os.path.join(root, "resized_256"))
+    for name, d in (("train.json", train), ("tiny.json", small), ("dev.json", small), ("test.json", small)):
+        with open(os.path.join(root, "imSitu", name), "w") as f:
+            json.dump(d, f)
+    g = torch.Generator().manual_seed(0)
+    for k in small:
+        arr = (torch.rand(256, 256, 3, generator=g) * 255).to(torch.uint8).numpy()
+        Image.fromarray(arr).save(os.path.join(root, "resized_256", k))
+    nouns = {lab: {"gloss": ["gloss_" + lab]} for fr in ann.values() for f in fr["frames"] for lab in f.values() if lab}
+    verbs = {v["verb"]: {"roles": {r: {} for r in v["frames"][0]}} for v in ann.values()}
+    with open(os.path.join(root, "imSitu", "imsitu_space.json"), "w") as f:
+        json.dump({"nouns": nouns, "verbs": verbs}, f)
+    return keys[0]
+
+
+@pytest.mark.gpu
+def test_all_modes_end_to_end(tmp_path, capsys, monkeypatch):
+    from situation_recognition_b200 import sr
+    first = _make_dataset(str(tmp_path))
+    monkeypatch.chdir(tmp_path)
+    common = ["--no_pretrained", "--num_workers", "0", "--batch_size", "4"]
+    sr.main(common + ["--train_file", "tiny.json", "--epochs", "1", "--model_saving_name", "tiny"])
+    out = capsys.readouterr().out
+    assert "Model training started!" in out and "Epoch-0, lr: 0.0020" in out
+    assert re.search(r"training losses = \[v: \d+\.\d\d, n: \d+\.\d\d, gt: \d+\.\d\d\]", out)
+    assert re.search(r"1-verb: \d+\.\d\d, 1-value: \d+\.\d\d, 1-value-all: \d+\.\d\d", out)
+    ckpt = torch.load(tmp_path / "checkpoints" / "tiny", weights_only=False)
+    assert set(ckpt) == {'epoch', 'avg_scores', 'verb_losses', 'nouns_losses', 'val_avg_scores', 'val_verb_losses',
+                         'val_nouns_losses', 'model_state_dict', 'optimizer_state_dict'}            # sr.py:145-157
+    assert ckpt['epoch'] == 1 and 'ggsnn.W_p.weight' in ckpt['model_state_dict']
+    assert 'convnet_verbs.model.conv1.weight' in ckpt['model_state_dict']
+    sr.main(common + ["--resume_model", "tiny", "--evaluate_dev"])
+    out = capsys.readouterr().out
+    assert "Loading encoder file" in out and "=> evaluating model with dev-set..." in out and "val losses = [v:" in out
+    sr.main(common + ["--resume_model", "tiny", "--test_img", os.path.join("resized_256", first)])
+    out = capsys.readouterr().out
+    assert "No ground truth verb found, calculating by myself..." in out and re.search(r"action \(\d+\.\d\d%\): verb\d+", out)
+    sr.main(common + ["--resume_model", "tiny", "--test_img", os.path.join("resized_256", first), "--verb", "verb003"])
+    assert "action (100.00%): verb003" in capsys.readouterr().out
+    sr.main(common + ["--resume_model", "tiny", "--subset", "2"])
+    out = capsys.readouterr().out
+    assert out.count("Analizing: ") == 2 and "---- Ground truth ----" in out
