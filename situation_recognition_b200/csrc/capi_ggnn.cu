@@ -26,19 +26,30 @@ struct srg_handle {
   int32_t* d_role_count = nullptr;
   bool tables_set = false;
   int* d_bad = nullptr;
-  // packed tensor-core operands
+  // ---- packed tensor-core operands (rebuilt by srg_pack_weights)
+  // The neighbour projection is folded into the gate weights:  (a W_p^T + c b_p) W_x^T = a (W_x W_p)^T + c W_x b_p,
+  // so the message GEMM disappears and the gates read the aggregated state `a` directly.  P_x = W_x W_p.
   int packed_prec = -1;
-  int alloc_split = 0;  // K replication factor the buffers were allocated for (1 or 3)
-  bf16 *Wp = nullptr, *Wzr = nullptr, *Wh = nullptr, *Wcn = nullptr, *Wcv = nullptr;
-  bf16 *Wm_stack = nullptr, *UW_stack = nullptr, *Uh = nullptr;
-  float *bp = nullptr, *bzr = nullptr, *bh = nullptr, *bcn = nullptr, *bcv = nullptr;
+  int alloc_split = 0;  // K replication factor the forward buffers were allocated for (1 or 6)
+  srg_params params;    // fp32 masters seen by the last srg_pack_weights (needed by the backward chain rule)
+  bf16 *Wzr = nullptr;  // [2D, 2D*s]  rows z|r, K blocks [P_x | U_x]
+  bf16 *Wh = nullptr;   // [D,  2D*s]  [P_h | U_h]
+  bf16 *Wcn = nullptr, *Wcv = nullptr;
+  bf16 *Wm_hi = nullptr, *Wm_mid = nullptr, *Wm_lo = nullptr;  // [3D, D] = [W_h; W_z; W_r] as bf16 hi + mid + lo parts
+  bf16 *Wp6 = nullptr;                                         // [6D, D] = W_p parts [hi; mid; hi; lo; hi; mid]
+  bf16 *P_hi = nullptr, *P_mid = nullptr, *P_lo = nullptr;     // [3D, D] = [P_h; P_z; P_r]
+  bf16 *U_stack = nullptr, *Uh = nullptr;   // [2D, D] = [U_z; U_r], [D, D]
+  float *wb = nullptr;                      // [3D] = [W_h b_p; W_z b_p; W_r b_p]
+  float *bzr[2] = {nullptr, nullptr};       // [2D] per mode (noun, verb): b_Wx + b_Ux + c W_x b_p
+  float *bh[2] = {nullptr, nullptr};        // [D]  per mode
+  float *bcn = nullptr, *bcv = nullptr;
 };
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------ workspace
 struct StepBufs {
-  bf16 *a_hi = nullptr, *a_lo = nullptr, *m_hi = nullptr, *m_lo = nullptr, *rh_hi = nullptr, *rh_lo = nullptr;
+  bf16 *a_hi = nullptr, *a_mid = nullptr, *a_lo = nullptr, *rh_hi = nullptr, *rh_mid = nullptr, *rh_lo = nullptr;
   bf16 *r = nullptr, *hc = nullptr;
   void* z = nullptr;
 };
@@ -47,14 +58,19 @@ struct PathBufs {
   int M = 0;
   float* h32 = nullptr;
   bf16* hb_hi[kMaxT + 1] = {};
+  bf16* hb_mid[kMaxT + 1] = {};
   bf16* hb_lo[kMaxT + 1] = {};
   StepBufs st[kMaxT];
-  bf16 *xd_hi = nullptr, *xd_lo = nullptr;
+  bf16 *xd_hi = nullptr, *xd_mid = nullptr, *xd_lo = nullptr;
   float* stats = nullptr;
   float* mask = nullptr;
   // backward
-  float *dh = nullptr, *dh_acc = nullptr, *da = nullptr;
-  bf16 *dpre_z[2] = {}, *dpre_h[2] = {}, *dpre_r = nullptr, *dm = nullptr, *adm = nullptr, *dlb = nullptr;
+  float *dh = nullptr, *dh_acc = nullptr, *dx = nullptr;
+  bf16* dpre[2] = {};  // [M, 3D] column blocks [dpre_h | dpre_z | dpre_r], ping-pong over steps
+  bf16 *da = nullptr, *ada = nullptr, *dlb = nullptr;
+  float* G_P = nullptr;   // [3D, D] fp32: d/dP_x accumulated over the steps of this path
+  bf16* G_Pb = nullptr;   // bf16 copy for the chain-rule GEMMs
+  float* s_all = nullptr; // [3D]: c * colsum(dpre_x), for the W_x b_p bias term
   size_t bytes = 0;
 };
 
@@ -86,13 +102,16 @@ PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* w
   pb.h32 = bump.take<float>(MD);
   const int n_hb = save ? T + 1 : 2;
   bf16* hbh[kMaxT + 1];
+  bf16* hbm[kMaxT + 1];
   bf16* hbl[kMaxT + 1];
   for (int i = 0; i < n_hb; ++i) {
     hbh[i] = bump.take<bf16>(MD);
+    hbm[i] = f32 ? bump.take<bf16>(MD) : nullptr;
     hbl[i] = f32 ? bump.take<bf16>(MD) : nullptr;
   }
   for (int t = 0; t <= T; ++t) {
     pb.hb_hi[t] = hbh[save ? t : (t & 1)];
+    pb.hb_mid[t] = hbm[save ? t : (t & 1)];
     pb.hb_lo[t] = hbl[save ? t : (t & 1)];
   }
   const int n_st = save ? T : 1;
@@ -101,11 +120,11 @@ PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* w
     StepBufs& s = sts[i];
     if (mode == SRG_MODE_NOUN) {
       s.a_hi = bump.take<bf16>(MD);
+      s.a_mid = f32 ? bump.take<bf16>(MD) : nullptr;
       s.a_lo = f32 ? bump.take<bf16>(MD) : nullptr;
     }
-    s.m_hi = bump.take<bf16>(MD);
-    s.m_lo = f32 ? bump.take<bf16>(MD) : nullptr;
     s.rh_hi = bump.take<bf16>(MD);
+    s.rh_mid = f32 ? bump.take<bf16>(MD) : nullptr;
     s.rh_lo = f32 ? bump.take<bf16>(MD) : nullptr;
     s.z = f32 ? static_cast<void*>(bump.take<float>(MD)) : static_cast<void*>(bump.take<bf16>(MD));
     if (save) {
@@ -115,21 +134,22 @@ PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* w
   }
   for (int t = 0; t < T; ++t) pb.st[t] = sts[save ? t : 0];
   pb.xd_hi = bump.take<bf16>(MD);
+  pb.xd_mid = f32 ? bump.take<bf16>(MD) : nullptr;
   pb.xd_lo = f32 ? bump.take<bf16>(MD) : nullptr;
   pb.stats = bump.take<float>(static_cast<size_t>(M) * (npad / 128) * 2);
   if (mode == SRG_MODE_NOUN) pb.mask = bump.take<float>(static_cast<size_t>(B) * h->R * h->R);
   if (save) {
     pb.dh = bump.take<float>(MD);
     pb.dh_acc = bump.take<float>(MD);
-    pb.da = bump.take<float>(MD);
-    for (int i = 0; i < 2; ++i) {
-      pb.dpre_z[i] = bump.take<bf16>(MD);
-      pb.dpre_h[i] = bump.take<bf16>(MD);
-    }
-    pb.dpre_r = bump.take<bf16>(MD);
-    pb.dm = bump.take<bf16>(MD);
-    pb.adm = (mode == SRG_MODE_NOUN) ? bump.take<bf16>(MD) : nullptr;
+    pb.dx = bump.take<float>(MD);
+    pb.dpre[0] = bump.take<bf16>(3 * MD);
+    pb.dpre[1] = bump.take<bf16>(3 * MD);
+    pb.da = bump.take<bf16>(MD);
+    pb.ada = (mode == SRG_MODE_NOUN) ? bump.take<bf16>(MD) : nullptr;
     pb.dlb = bump.take<bf16>(static_cast<size_t>(M) * npad);
+    pb.G_P = bump.take<float>(static_cast<size_t>(3) * D * D);
+    pb.G_Pb = bump.take<bf16>(static_cast<size_t>(3) * D * D);
+    pb.s_all = bump.take<float>(static_cast<size_t>(3) * D);
   }
   pb.bytes = bump.off + 1024;
   return pb;
@@ -158,20 +178,33 @@ GemmProblem base_problem(const srg_handle* h, int M, int N) {
   return p;
 }
 
-void add_seg(GemmProblem& p, const bf16* a, int64_t rows, int64_t cols, int k_off, int k_len) {
+void add_seg_ld(GemmProblem& p, const bf16* a, int64_t rows, int64_t cols, int64_t ld, int k_off, int k_len) {
   GemmSeg& s = p.seg[p.nseg++];
-  s.a = mat(a, rows, cols, cols, DT_BF16);
+  s.a = mat(a, rows, cols, ld, DT_BF16);
   s.k_off = k_off;
   s.k_len = k_len;
 }
+void add_seg(GemmProblem& p, const bf16* a, int64_t rows, int64_t cols, int k_off, int k_len) {
+  add_seg_ld(p, a, rows, cols, cols, k_off, k_len);
+}
 
-// A = [x0 | x1 | ...] (each [M, D]) -- in fp32 mode replicated as (hi.., hi.., lo..) to meet B = [hi | lo | hi]
-void add_split_segs(GemmProblem& p, int M, int D, bool f32, const bf16* const* hi, const bf16* const* lo, int n) {
-  for (int i = 0; i < n; ++i) add_seg(p, hi[i], M, D, 0, D);
-  if (f32) {
-    for (int i = 0; i < n; ++i) add_seg(p, hi[i], M, D, 0, D);
-    for (int i = 0; i < n; ++i) add_seg(p, lo[i], M, D, 0, D);
-  }
+// fp32-parity arithmetic: every operand is x = hi + mid + lo (three bf16 parts, 24 significant bits) and a product is
+// expanded into the six terms of weight >= 2^-16:  hi*hi + hi*mid + mid*hi + hi*lo + lo*hi + mid*mid.
+// K block b of the packed weights holds part kPartB[b]; the activation segments carry part kPartA[b].
+constexpr int kSplitTerms = 6;
+constexpr int kPartA[kSplitTerms] = {0, 0, 1, 0, 2, 1};
+constexpr int kPartB[kSplitTerms] = {0, 1, 0, 2, 0, 1};
+
+struct Split3 {
+  const bf16* part[3];
+};
+
+// A = [x0 | x1 | ...] (each [M, D]), replicated per split term in fp32 mode
+void add_split_segs(GemmProblem& p, int M, int D, bool f32, const Split3* x, int n) {
+  const int terms = f32 ? kSplitTerms : 1;
+  for (int b = 0; b < terms; ++b)
+    for (int i = 0; i < n; ++i) add_seg(p, x[i].part[kPartA[b]], M, D, 0, D);
+  if (f32) p.corr_seg_begin = n;   // term 0 (hi*hi) -> main accumulator, terms 1..5 -> correction accumulator
 }
 
 int wgrad_splits(const srg_handle* h, int out_rows, int out_cols, int K) {
@@ -186,15 +219,16 @@ int wgrad_splits(const srg_handle* h, int out_rows, int out_cols, int K) {
   return s;
 }
 
-// dW[out, in] += dY^T[out, M] * X[M, in]   (both operands MN-major, split-K, TMA reduce-add)
-int wgrad(const srg_handle* h, const bf16* dY, int64_t dy_cols, int out_rows, const bf16* X, int in_cols, int M,
+// dW[out, in] += dY^T[out, M] * X[M, in]   (both operands MN-major, split-K, TMA reduce-add).
+// dY is a column block (out_rows columns, leading dimension dy_ld) of a wider matrix.
+int wgrad(const srg_handle* h, const bf16* dY, int64_t dy_ld, int out_rows, const bf16* X, int in_cols, int M,
           float* dW, cudaStream_t s) {
   if (dW == nullptr) return SRG_OK;
   GemmProblem p = base_problem(h, out_rows, in_cols);
   p.a_mn = true;
   p.b_mn = true;
   p.nseg = 1;
-  p.seg[0].a = mat(dY, M, dy_cols, dy_cols, DT_BF16);
+  p.seg[0].a = mat(dY, M, out_rows, dy_ld, DT_BF16);
   p.seg[0].k_off = 0;
   p.seg[0].k_len = M;
   p.b = mat(X, M, in_cols, in_cols, DT_BF16);
@@ -210,60 +244,54 @@ int ggnn_steps(srg_handle* h, int mode, PathBufs& pb, float* h32, const float* m
                cudaStream_t s) {
   const int D = h->D, T = h->T, M = pb.M;
   const bool f32 = (prec == SRG_PREC_FP32);
-  const int kmul = f32 ? 3 : 1;
+  const int kmul = f32 ? kSplitTerms : 1;
+  const int mi = (mode == SRG_MODE_NOUN) ? 0 : 1;
   for (int t = 0; t < T; ++t) {
     StepBufs& st = pb.st[t];
-    const bf16* ain_hi = pb.hb_hi[t];
-    const bf16* ain_lo = pb.hb_lo[t];
+    // aggregated neighbour state a[b,i] = sum_j mask[b,i,j] h[b,j]  (model.py:67-75); verb mode: a = h (62-64)
+    const Split3 hcur = {{pb.hb_hi[t], pb.hb_mid[t], pb.hb_lo[t]}};
+    Split3 a = hcur;
     if (mode == SRG_MODE_NOUN) {
-      SRG_TRY(launch_aggregate(h32, mask, B, h->R, D, st.a_hi, st.a_lo, s));
-      ain_hi = st.a_hi;
-      ain_lo = st.a_lo;
+      SRG_TRY(launch_aggregate(h32, mask, B, h->R, D, st.a_hi, st.a_mid, st.a_lo, s));
+      a = Split3{{st.a_hi, st.a_mid, st.a_lo}};
     }
-    {  // message: m = a W_p^T + (R | 1) b_p      (model.py:62-64 | 67-77)
-      GemmProblem p = base_problem(h, M, D);
-      add_split_segs(p, M, D, f32, &ain_hi, &ain_lo, 1);
-      p.b = mat(h->Wp, D, static_cast<int64_t>(D) * kmul, static_cast<int64_t>(D) * kmul, DT_BF16);
-      p.epi = EPI_STORE_BF16;
-      p.bias = h->bp;
-      p.bias_scale = (mode == SRG_MODE_NOUN) ? static_cast<float>(h->R) : 1.0f;
-      p.flags = f32 ? FLAG_LO : 0;
-      p.io[0] = mat(st.m_hi, M, D, D, DT_BF16);
-      if (f32) p.io[1] = mat(st.m_lo, M, D, D, DT_BF16);
-      SRG_TRY(run_gemm(p, h->dev, s));
-    }
-    {  // gates: [z | r] = sigmoid([m | h] [W_z U_z ; W_r U_r]^T + b), rh = r * h      (model.py:80-81)
+    const Split3 rh = {{st.rh_hi, st.rh_mid, st.rh_lo}};
+    {  // gates: [z | r] = sigmoid([a | h] [P_z U_z ; P_r U_r]^T + b'), rh = r * h      (model.py:74,80-81)
       GemmProblem p = base_problem(h, M, 2 * D);
-      const bf16* hi[2] = {st.m_hi, pb.hb_hi[t]};
-      const bf16* lo[2] = {st.m_lo, pb.hb_lo[t]};
-      add_split_segs(p, M, D, f32, hi, lo, 2);
+      const Split3 ops[2] = {a, hcur};
+      add_split_segs(p, M, D, f32, ops, 2);
       p.b = mat(h->Wzr, 2 * D, static_cast<int64_t>(2 * D) * kmul, static_cast<int64_t>(2 * D) * kmul, DT_BF16);
       p.epi = EPI_ZR;
       p.f32 = f32;
-      p.bias = h->bzr;
+      p.bias = h->bzr[mi];
       p.n_split = D;
       p.flags = (f32 ? FLAG_LO : 0) | (save ? FLAG_STASH : 0);
       p.io[0] = mat(st.z, M, D, D, f32 ? DT_F32 : DT_BF16);
       p.io[1] = mat(h32, M, D, D, DT_F32);
       p.io[2] = mat(st.rh_hi, M, D, D, DT_BF16);
-      if (f32) p.io[3] = mat(st.rh_lo, M, D, D, DT_BF16);
+      if (f32) {
+        p.io[3] = mat(st.rh_mid, M, D, D, DT_BF16);
+        p.io[5] = mat(st.rh_lo, M, D, D, DT_BF16);
+      }
       if (save) p.io[4] = mat(st.r, M, D, D, DT_BF16);
       SRG_TRY(run_gemm(p, h->dev, s));
     }
-    {  // candidate + update: h' = h + z * (tanh([m | rh] [W_h U_h]^T + b) - h)      (model.py:82-84)
+    {  // candidate + update: h' = h + z * (tanh([a | rh] [P_h U_h]^T + b') - h)      (model.py:82-84)
       GemmProblem p = base_problem(h, M, D);
-      const bf16* hi[2] = {st.m_hi, st.rh_hi};
-      const bf16* lo[2] = {st.m_lo, st.rh_lo};
-      add_split_segs(p, M, D, f32, hi, lo, 2);
+      const Split3 ops[2] = {a, rh};
+      add_split_segs(p, M, D, f32, ops, 2);
       p.b = mat(h->Wh, D, static_cast<int64_t>(2 * D) * kmul, static_cast<int64_t>(2 * D) * kmul, DT_BF16);
       p.epi = EPI_H;
       p.f32 = f32;
-      p.bias = h->bh;
+      p.bias = h->bh[mi];
       p.flags = save ? FLAG_STASH : 0;
       p.io[0] = mat(h32, M, D, D, DT_F32);
       p.io[1] = mat(st.z, M, D, D, f32 ? DT_F32 : DT_BF16);
       p.io[2] = mat(pb.hb_hi[t + 1], M, D, D, DT_BF16);
-      if (f32) p.io[3] = mat(pb.hb_lo[t + 1], M, D, D, DT_BF16);
+      if (f32) {
+        p.io[3] = mat(pb.hb_mid[t + 1], M, D, D, DT_BF16);
+        p.io[5] = mat(pb.hb_lo[t + 1], M, D, D, DT_BF16);
+      }
       if (save) p.io[4] = mat(st.hc, M, D, D, DT_BF16);
       SRG_TRY(run_gemm(p, h->dev, s));
     }
@@ -275,24 +303,24 @@ int classifier_forward(srg_handle* h, int mode, PathBufs& pb, const float* h32, 
                        float* logits, int64_t ldl, int prec, cudaStream_t s) {
   const int D = h->D, M = pb.M;
   const bool f32 = (prec == SRG_PREC_FP32);
-  const int kmul = f32 ? 3 : 1;
+  const int kmul = f32 ? kSplitTerms : 1;
   const int ncls = (mode == SRG_MODE_NOUN) ? h->L : h->V;
   const int npad = (mode == SRG_MODE_NOUN) ? h->Lpad : h->Vpad;
   SRG_CHECK(ldl >= ncls && (ldl % 4) == 0, "logits leading dimension %lld must be >= %d and a multiple of 4",
             (long long)ldl, ncls);
   SRG_CHECK(drop_p >= 0.f && drop_p < 1.f, "dropout probability %f out of range", drop_p);
-  const bf16* x_hi = pb.hb_hi[h->T];
-  const bf16* x_lo = pb.hb_lo[h->T];
+  Split3 x = {{pb.hb_hi[h->T], pb.hb_mid[h->T], pb.hb_lo[h->T]}};
   if (keep != nullptr && drop_p > 0.f) {
-    SRG_TRY(launch_dropout_cast(h32, keep, 1.0f / (1.0f - drop_p), static_cast<int64_t>(M) * D, pb.xd_hi, pb.xd_lo, s));
-    x_hi = pb.xd_hi;
-    x_lo = pb.xd_lo;
+    SRG_TRY(launch_dropout_cast(h32, keep, 1.0f / (1.0f - drop_p), static_cast<int64_t>(M) * D, pb.xd_hi, pb.xd_mid,
+                                pb.xd_lo, s));
+    x = Split3{{pb.xd_hi, pb.xd_mid, pb.xd_lo}};
   }
   GemmProblem p = base_problem(h, M, npad);
-  add_split_segs(p, M, D, f32, &x_hi, &x_lo, 1);
+  add_split_segs(p, M, D, f32, &x, 1);
   const bf16* W = (mode == SRG_MODE_NOUN) ? h->Wcn : h->Wcv;
   p.b = mat(W, npad, static_cast<int64_t>(D) * kmul, static_cast<int64_t>(D) * kmul, DT_BF16);
   p.epi = EPI_LOGITS;
+  p.f32 = f32;
   p.bias = (mode == SRG_MODE_NOUN) ? h->bcn : h->bcv;
   p.n_valid = ncls;
   p.stats = pb.stats;
@@ -301,10 +329,6 @@ int classifier_forward(srg_handle* h, int mode, PathBufs& pb, const float* h32, 
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-struct PathGrads {
-  float *Wc, *bc;
-};
-
 int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, int64_t ldl, int B,
                   const uint8_t* keep, float drop_p, const srg_grads* g, cudaStream_t s) {
   const int D = h->D, T = h->T, M = pb.M, R = h->R;
@@ -314,8 +338,13 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
   float* gWc = (mode == SRG_MODE_NOUN) ? g->Wc_noun : g->Wc_verb;
   float* gbc = (mode == SRG_MODE_NOUN) ? g->bc_noun : g->bc_verb;
   const int64_t MD = static_cast<int64_t>(M) * D;
+  const int64_t ld3 = 3 * static_cast<int64_t>(D);
+  const float cmul = (mode == SRG_MODE_NOUN) ? static_cast<float>(R) : 1.f;  // how often b_p enters a message
   const bool use_drop = (keep != nullptr && drop_p > 0.f);
   const bf16* x = use_drop ? pb.xd_hi : pb.hb_hi[T];
+
+  SRG_CUDA(cudaMemsetAsync(pb.G_P, 0, sizeof(float) * 3 * D * D, s));
+  SRG_CUDA(cudaMemsetAsync(pb.s_all, 0, sizeof(float) * 3 * D, s));
 
   // ---- classifier (model.py:105-111,152,168)
   SRG_TRY(launch_cast_pad(dlogits, ldl, M, ncls, npad, pb.dlb, s));
@@ -327,92 +356,120 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
     p.b_mn = true;
     p.b = mat(Wc, npad, D, D, DT_BF16);
     p.epi = EPI_STORE_F32;
-    p.io[0] = mat(use_drop ? pb.da : pb.dh, M, D, D, DT_F32);
+    p.io[0] = mat(use_drop ? pb.dx : pb.dh, M, D, D, DT_F32);
     SRG_TRY(run_gemm(p, h->dev, s));
-    if (use_drop) SRG_TRY(launch_dropout_bwd(pb.da, keep, 1.0f / (1.0f - drop_p), MD, pb.dh, s));
+    if (use_drop) SRG_TRY(launch_dropout_bwd(pb.dx, keep, 1.0f / (1.0f - drop_p), MD, pb.dh, s));
   }
 
-  // dL/dh' of the last step comes from the classifier; from there on every step's "pre" work (GRU-gate derivatives of
-  // step t-1) is fused into the epilogue of the GEMM that completes dL/dh of step t (EPI_DH).
+  // dL/dh' of the last step comes from the classifier; from there on the GRU-gate derivatives of step t-1 are fused
+  // into the epilogue of the GEMM that completes dL/dh of step t (EPI_DH).
+  // dpre[cur] = [dpre_h | dpre_z | dpre_r] as column blocks of one [M, 3D] matrix.
   float* dh_acc = pb.dh_acc;
   int cur = 0;
-  SRG_TRY(launch_gru_bwd_pre(pb.dh, static_cast<const bf16*>(pb.st[T - 1].z), pb.st[T - 1].hc, pb.hb_hi[T - 1], MD,
-                             pb.dpre_z[cur], pb.dpre_h[cur], dh_acc, s));
+  SRG_TRY(launch_gru_bwd_pre_ld(pb.dh, static_cast<const bf16*>(pb.st[T - 1].z), pb.st[T - 1].hc, pb.hb_hi[T - 1], M, D,
+                                pb.dpre[cur] + D, pb.dpre[cur], ld3, dh_acc, s));
   for (int t = T - 1; t >= 0; --t) {
     StepBufs& st = pb.st[t];
-    bf16* dpre_z = pb.dpre_z[cur];
-    bf16* dpre_h = pb.dpre_h[cur];
+    bf16* dp = pb.dpre[cur];
+    bf16* dpre_h = dp;
+    bf16* dpre_z = dp + D;
+    bf16* dpre_r = dp + 2 * D;
     {  // d(r*h) = dpre_h U_h ; fused: dpre_r = drh*h*r*(1-r), dh_acc += drh*r
       GemmProblem p = base_problem(h, M, D);
-      add_seg(p, dpre_h, M, D, 0, D);
+      add_seg_ld(p, dp, M, ld3, ld3, 0, D);
       p.b_mn = true;
       p.b = mat(h->Uh, D, D, D, DT_BF16);
       p.epi = EPI_DRH;
       p.io[0] = mat(pb.hb_hi[t], M, D, D, DT_BF16);
       p.io[1] = mat(st.r, M, D, D, DT_BF16);
-      p.io[2] = mat(pb.dpre_r, M, D, D, DT_BF16);
+      p.io[2] = mat(dpre_r, M, D, ld3, DT_BF16);
       p.io[3] = mat(dh_acc, M, D, D, DT_F32);
       SRG_TRY(run_gemm(p, h->dev, s));
     }
-    {  // dm = [dpre_h | dpre_z | dpre_r] [W_h ; W_z ; W_r]
+    {  // da = [dpre_h | dpre_z | dpre_r] [P_h ; P_z ; P_r]   (gradient w.r.t. the aggregated state)
       GemmProblem p = base_problem(h, M, D);
-      add_seg(p, dpre_h, M, D, 0, D);
-      add_seg(p, dpre_z, M, D, 0, D);
-      add_seg(p, pb.dpre_r, M, D, 0, D);
+      add_seg_ld(p, dp, M, ld3, ld3, 0, 3 * D);
       p.b_mn = true;
-      p.b = mat(h->Wm_stack, 3 * D, D, D, DT_BF16);
+      p.b = mat(h->P_hi, 3 * D, D, D, DT_BF16);
       p.epi = EPI_STORE_BF16;
-      p.io[0] = mat(pb.dm, M, D, D, DT_BF16);
+      p.io[0] = mat(pb.da, M, D, D, DT_BF16);
       SRG_TRY(run_gemm(p, h->dev, s));
     }
-    // the aggregation is linear and commutes with W_p: push dm through its transpose first (noun mode)
-    const bf16* adm = pb.dm;
-    if (mode == SRG_MODE_NOUN) {
-      SRG_TRY(launch_aggregate_t_bf16(pb.dm, pb.mask, B, R, D, pb.adm, s));
-      adm = pb.adm;
+    const bf16* ada = pb.da;
+    if (mode == SRG_MODE_NOUN) {  // back through the aggregation: ada[b,j] = sum_i mask[b,i,j] da[b,i]
+      SRG_TRY(launch_aggregate_t_bf16(pb.da, pb.mask, B, R, D, pb.ada, s));
+      ada = pb.ada;
     }
-    {  // dL/dh_t = dh_acc + [dpre_z | dpre_r | adm] [U_z ; U_r ; W_p], then the gate derivatives of step t-1
+    {  // dL/dh_t = dh_acc + ada + [dpre_z | dpre_r] [U_z ; U_r], then the gate derivatives of step t-1
       GemmProblem p = base_problem(h, M, D);
-      add_seg(p, dpre_z, M, D, 0, D);
-      add_seg(p, pb.dpre_r, M, D, 0, D);
-      add_seg(p, adm, M, D, 0, D);
+      add_seg_ld(p, dp, M, ld3, ld3, D, 2 * D);
       p.b_mn = true;
-      p.b = mat(h->UW_stack, 3 * D, D, D, DT_BF16);
+      p.b = mat(h->U_stack, 2 * D, D, D, DT_BF16);
       p.epi = EPI_DH;
+      p.flags = FLAG_ADD;
       p.io[0] = mat(dh_acc, M, D, D, DT_F32);
+      p.io[6] = mat(ada, M, D, D, DT_BF16);
       if (t > 0) {
-        p.flags = FLAG_NEXT;
+        bf16* dn = pb.dpre[cur ^ 1];
+        p.flags |= FLAG_NEXT;
         p.io[1] = mat(pb.st[t - 1].z, M, D, D, DT_BF16);
         p.io[2] = mat(pb.st[t - 1].hc, M, D, D, DT_BF16);
         p.io[3] = mat(pb.hb_hi[t - 1], M, D, D, DT_BF16);
-        p.io[4] = mat(pb.dpre_z[cur ^ 1], M, D, D, DT_BF16);
-        p.io[5] = mat(pb.dpre_h[cur ^ 1], M, D, D, DT_BF16);
+        p.io[4] = mat(dn + D, M, D, ld3, DT_BF16);  // dpre_z of step t-1
+        p.io[5] = mat(dn, M, D, ld3, DT_BF16);      // dpre_h of step t-1
       }
       SRG_TRY(run_gemm(p, h->dev, s));
     }
-    // ---- weight gradients of this step (the 7 linears are shared by all steps and both paths: accumulate)
-    const bf16* msg_in = (mode == SRG_MODE_NOUN) ? st.a_hi : pb.hb_hi[t];
-    SRG_TRY(wgrad(h, pb.dm, D, D, msg_in, D, M, g->W_p, s));
-    SRG_TRY(wgrad(h, dpre_z, D, D, st.m_hi, D, M, g->W_z, s));
-    SRG_TRY(wgrad(h, dpre_z, D, D, pb.hb_hi[t], D, M, g->U_z, s));
-    SRG_TRY(wgrad(h, pb.dpre_r, D, D, st.m_hi, D, M, g->W_r, s));
-    SRG_TRY(wgrad(h, pb.dpre_r, D, D, pb.hb_hi[t], D, M, g->U_r, s));
-    SRG_TRY(wgrad(h, dpre_h, D, D, st.m_hi, D, M, g->W_h, s));
-    SRG_TRY(wgrad(h, dpre_h, D, D, st.rh_hi, D, M, g->U_h, s));
-    ColsumJob jobs[4] = {{dpre_z, g->b_Wz, g->b_Uz, 1.f},
-                         {pb.dpre_r, g->b_Wr, g->b_Ur, 1.f},
-                         {dpre_h, g->b_Wh, g->b_Uh, 1.f},
-                         {pb.dm, g->b_p, nullptr, (mode == SRG_MODE_NOUN) ? static_cast<float>(R) : 1.f}};
-    SRG_TRY(launch_colsum_multi(jobs, 4, D, M, D, s));
+    // ---- weight gradients of this step
+    const bf16* a_in = (mode == SRG_MODE_NOUN) ? st.a_hi : pb.hb_hi[t];
+    SRG_TRY(wgrad(h, dp, ld3, 3 * D, a_in, D, M, pb.G_P, s));              // dP_h, dP_z, dP_r in one GEMM
+    SRG_TRY(wgrad(h, dpre_z, ld3, D, pb.hb_hi[t], D, M, g->U_z, s));
+    SRG_TRY(wgrad(h, dpre_r, ld3, D, pb.hb_hi[t], D, M, g->U_r, s));
+    SRG_TRY(wgrad(h, dpre_h, ld3, D, st.rh_hi, D, M, g->U_h, s));
+    ColsumJob jobs[3] = {{dpre_h, g->b_Wh, g->b_Uh, 1.f, pb.s_all, cmul},
+                         {dpre_z, g->b_Wz, g->b_Uz, 1.f, pb.s_all + D, cmul},
+                         {dpre_r, g->b_Wr, g->b_Ur, 1.f, pb.s_all + 2 * D, cmul}};
+    SRG_TRY(launch_colsum_multi(jobs, 3, ld3, M, D, s));
     cur ^= 1;
   }
-  float* dh = dh_acc;
-  pb.dh = dh;  // gradient w.r.t. the initial node states
+  pb.dh = dh_acc;  // gradient w.r.t. the initial node states
+
+  // ---- chain rule through P_x = W_x W_p and b'_x = b_Wx + b_Ux + c W_x b_p   (x = h, z, r)
+  SRG_TRY(launch_split_cast(pb.G_P, static_cast<int64_t>(3) * D * D, pb.G_Pb, nullptr, nullptr, s));
+  float* gW[3] = {g->W_h, g->W_z, g->W_r};
+  const float* W32[3] = {h->params.W_h, h->params.W_z, h->params.W_r};
+  for (int x3 = 0; x3 < 3; ++x3) {
+    if (gW[x3] != nullptr) {  // dW_x += dP_x W_p^T  + s_x (x) b_p
+      GemmProblem p = base_problem(h, D, D);
+      add_seg(p, pb.G_Pb + static_cast<size_t>(x3) * D * D, D, D, 0, D);
+      p.b = mat(h->Wp6, D, D, D, DT_BF16);  // first block of Wp6 = bf16(W_p), K-major [k, i]
+      p.epi = EPI_STORE_F32;
+      p.flags = FLAG_REDUCE;
+      p.io[0] = mat(gW[x3], D, D, D, DT_F32);
+      SRG_TRY(run_gemm(p, h->dev, s));
+      SRG_TRY(launch_outer_acc(pb.s_all + x3 * D, h->params.b_p, D, D, gW[x3], s));
+    }
+    if (g->b_p != nullptr) SRG_TRY(launch_matvec_t_acc(W32[x3], pb.s_all + x3 * D, D, D, g->b_p, s));
+  }
+  if (g->W_p != nullptr) {  // dW_p += [W_h; W_z; W_r]^T [dP_h; dP_z; dP_r]
+    GemmProblem p = base_problem(h, D, D);
+    p.a_mn = true;
+    p.b_mn = true;
+    p.nseg = 1;
+    p.seg[0].a = mat(h->Wm_hi, 3 * D, D, D, DT_BF16);
+    p.seg[0].k_off = 0;
+    p.seg[0].k_len = 3 * D;
+    p.b = mat(pb.G_Pb, 3 * D, D, D, DT_BF16);
+    p.epi = EPI_STORE_F32;
+    p.flags = FLAG_REDUCE;
+    p.io[0] = mat(g->W_p, D, D, D, DT_F32);
+    p.k_splits = wgrad_splits(h, D, D, 3 * D);
+    SRG_TRY(run_gemm(p, h->dev, s));
+  }
   return SRG_OK;
 }
 
 int ensure_pack_buffers(srg_handle* h, int split) {
-  if (h->alloc_split >= split) return SRG_OK;
   const size_t D = h->D;
   auto re = [&](bf16** p, size_t n) -> int {
     if (*p) cudaFree(*p);
@@ -420,22 +477,41 @@ int ensure_pack_buffers(srg_handle* h, int split) {
     SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(bf16)));
     return SRG_OK;
   };
-  SRG_TRY(re(&h->Wp, D * D * split));
+  auto f32buf = [&](float** p, size_t n) -> int {
+    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(float)));
+    return SRG_OK;
+  };
+  if (!h->Wm_hi) {
+    SRG_TRY(re(&h->Wm_hi, 3 * D * D));
+    SRG_TRY(re(&h->Wm_mid, 3 * D * D));
+    SRG_TRY(re(&h->Wm_lo, 3 * D * D));
+    SRG_TRY(re(&h->Wp6, 6 * D * D));
+    SRG_TRY(re(&h->P_hi, 3 * D * D));
+    SRG_TRY(re(&h->P_mid, 3 * D * D));
+    SRG_TRY(re(&h->P_lo, 3 * D * D));
+    SRG_TRY(re(&h->U_stack, 2 * D * D));
+    SRG_TRY(re(&h->Uh, D * D));
+    SRG_TRY(f32buf(&h->wb, 3 * D));
+    for (int i = 0; i < 2; ++i) {
+      SRG_TRY(f32buf(&h->bzr[i], 2 * D));
+      SRG_TRY(f32buf(&h->bh[i], D));
+    }
+    SRG_TRY(f32buf(&h->bcn, h->Lpad));
+    SRG_TRY(f32buf(&h->bcv, h->Vpad));
+  }
+  if (h->alloc_split >= split) return SRG_OK;
   SRG_TRY(re(&h->Wzr, 2 * D * 2 * D * split));
   SRG_TRY(re(&h->Wh, D * 2 * D * split));
   SRG_TRY(re(&h->Wcn, static_cast<size_t>(h->Lpad) * D * split));
   SRG_TRY(re(&h->Wcv, static_cast<size_t>(h->Vpad) * D * split));
-  if (!h->Wm_stack) {
-    SRG_TRY(re(&h->Wm_stack, 3 * D * D));
-    SRG_TRY(re(&h->UW_stack, 3 * D * D));
-    SRG_TRY(re(&h->Uh, D * D));
-    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->bp), D * sizeof(float)));
-    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->bzr), 2 * D * sizeof(float)));
-    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->bh), D * sizeof(float)));
-    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->bcn), h->Lpad * sizeof(float)));
-    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->bcv), h->Vpad * sizeof(float)));
-  }
   h->alloc_split = split;
+  return SRG_OK;
+}
+
+// dst[rows 0..D, col_off .. col_off+D] (leading dimension ld) <- src[D, D]
+int copy_block(bf16* dst, int64_t ld, int64_t row_off, int64_t col_off, const bf16* src, int D, cudaStream_t s) {
+  SRG_CUDA(cudaMemcpy2DAsync(dst + row_off * ld + col_off, ld * sizeof(bf16), src, D * sizeof(bf16), D * sizeof(bf16), D,
+                             cudaMemcpyDeviceToDevice, s));
   return SRG_OK;
 }
 
@@ -474,8 +550,8 @@ int srg_create(srg_handle** out, int device, int D, int R, int T, int n_verbs, i
 
 int srg_destroy(srg_handle* h) {
   if (!h) return SRG_OK;
-  void* ptrs[] = {h->d_verb2roles, h->d_role_count, h->d_bad, h->Wp, h->Wzr, h->Wh, h->Wcn, h->Wcv, h->Wm_stack,
-                  h->UW_stack, h->Uh, h->bp, h->bzr, h->bh, h->bcn, h->bcv};
+  void* ptrs[] = {h->d_verb2roles, h->d_role_count, h->d_bad, h->Wzr, h->Wh, h->Wcn, h->Wcv, h->Wm_hi, h->Wm_mid, h->Wm_lo, h->Wp6,
+                  h->P_hi, h->P_mid, h->P_lo, h->U_stack, h->Uh, h->wb, h->bzr[0], h->bzr[1], h->bh[0], h->bh[1], h->bcn, h->bcv};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete h;
@@ -519,44 +595,77 @@ int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* st
   SRG_CHECK(precision == SRG_PREC_BF16 || precision == SRG_PREC_FP32, "bad precision %d", precision);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int D = h->D;
-  const int split = (precision == SRG_PREC_FP32) ? 3 : 1;
+  const int split = (precision == SRG_PREC_FP32) ? kSplitTerms : 1;
   SRG_TRY(ensure_pack_buffers(h, split));
-  // K layout per weight group: [hi-block | lo-block | hi-block] (fp32 mode) or [hi-block] (bf16 mode);
-  // a block holds the concatenated inputs of that GEMM, e.g. [W_z | U_z].
-  auto pack = [&](const float* src, int rows, int rows_pad, bf16* dst, int64_t ld, int64_t row_off, int block_cols,
-                  int col_in_block) -> int {
+  h->params = *p;
+  const size_t DD = static_cast<size_t>(D) * D;
+
+  // (1) bf16 parts (hi, mid, lo) of the message-side weights, stacked [W_h; W_z; W_r], and of W_p in block order kPartB
+  const float* Wm32[3] = {p->W_h, p->W_z, p->W_r};
+  bf16* Wm_part[3] = {h->Wm_hi, h->Wm_mid, h->Wm_lo};
+  for (int x = 0; x < 3; ++x)
+    for (int part = 0; part < 3; ++part)
+      SRG_TRY(launch_pack_weight(Wm32[x], D, D, D, Wm_part[part] + x * DD, D, 0, part, s));
+  for (int b = 0; b < kSplitTerms; ++b)
+    SRG_TRY(launch_pack_weight(p->W_p, D, D, D, h->Wp6 + b * DD, D, 0, kPartB[b], s));
+
+  // (2) P = [W_h; W_z; W_r] W_p, fp32-accurate through the split (3 leading terms are enough for the bf16 operands of
+  //     the training mode, all 6 for the fp32-parity mode), written as bf16 hi + mid + lo
+  {
+    const int terms = (precision == SRG_PREC_FP32) ? kSplitTerms : 3;
+    GemmProblem g = base_problem(h, 3 * D, D);
+    for (int b = 0; b < terms; ++b) add_seg(g, Wm_part[kPartA[b]], 3 * D, D, 0, D);
+    g.corr_seg_begin = 1;
+    g.b_mn = true;                                   // B[n = i, k] = W_p[k, i]: W_p as stored, K along rows
+    g.b = mat(h->Wp6, static_cast<int64_t>(terms) * D, D, D, DT_BF16);
+    g.epi = EPI_STORE_BF16;
+    g.f32 = true;                                    // instantiation with the 3-way split output
+    g.flags = FLAG_LO;
+    g.io[0] = mat(h->P_hi, 3 * D, D, D, DT_BF16);
+    g.io[1] = mat(h->P_mid, 3 * D, D, D, DT_BF16);
+    g.io[2] = mat(h->P_lo, 3 * D, D, D, DT_BF16);
+    SRG_TRY(run_gemm(g, h->dev, s));
+  }
+
+  // (3) forward operands: K blocks [P_x | U_x], one block per split term (part kPartB[b]) in fp32 mode
+  const int64_t ld1 = static_cast<int64_t>(D) * split, ld2 = static_cast<int64_t>(2 * D) * split;
+  const bf16* P_part[3] = {h->P_hi, h->P_mid, h->P_lo};
+  auto pack_u = [&](const float* src, int rows, int rows_pad, bf16* dst, int64_t ld, int64_t row_off, int block_cols,
+                    int col_in_block) -> int {
     bf16* d = dst + row_off * ld;
-    SRG_TRY(launch_pack_weight(src, rows, D, rows_pad, d, ld, col_in_block, 0, s));
-    if (split == 3) {
-      SRG_TRY(launch_pack_weight(src, rows, D, rows_pad, d, ld, block_cols + col_in_block, 1, s));
-      SRG_TRY(launch_pack_weight(src, rows, D, rows_pad, d, ld, 2 * block_cols + col_in_block, 0, s));
-    }
+    for (int b = 0; b < split; ++b)
+      SRG_TRY(launch_pack_weight(src, rows, D, rows_pad, d, ld, static_cast<int64_t>(b) * block_cols + col_in_block,
+                                 kPartB[b], s));
     return SRG_OK;
   };
-  const int64_t ld1 = static_cast<int64_t>(D) * split, ld2 = static_cast<int64_t>(2 * D) * split;
-  SRG_TRY(pack(p->W_p, D, D, h->Wp, ld1, 0, D, 0));
-  SRG_TRY(pack(p->W_z, D, D, h->Wzr, ld2, 0, 2 * D, 0));
-  SRG_TRY(pack(p->U_z, D, D, h->Wzr, ld2, 0, 2 * D, D));
-  SRG_TRY(pack(p->W_r, D, D, h->Wzr, ld2, D, 2 * D, 0));
-  SRG_TRY(pack(p->U_r, D, D, h->Wzr, ld2, D, 2 * D, D));
-  SRG_TRY(pack(p->W_h, D, D, h->Wh, ld2, 0, 2 * D, 0));
-  SRG_TRY(pack(p->U_h, D, D, h->Wh, ld2, 0, 2 * D, D));
-  SRG_TRY(pack(p->Wc_noun, h->L, h->Lpad, h->Wcn, ld1, 0, D, 0));
-  SRG_TRY(pack(p->Wc_verb, h->V, h->Vpad, h->Wcv, ld1, 0, D, 0));
-  if (precision == SRG_PREC_BF16) {
-    // backward operands (MN-major B = stacks along K)
-    SRG_TRY(launch_pack_weight(p->W_h, D, D, D, h->Wm_stack, D, 0, 0, s));
-    SRG_TRY(launch_pack_weight(p->W_z, D, D, D, h->Wm_stack + static_cast<size_t>(D) * D, D, 0, 0, s));
-    SRG_TRY(launch_pack_weight(p->W_r, D, D, D, h->Wm_stack + 2 * static_cast<size_t>(D) * D, D, 0, 0, s));
-    SRG_TRY(launch_pack_weight(p->U_z, D, D, D, h->UW_stack, D, 0, 0, s));
-    SRG_TRY(launch_pack_weight(p->U_r, D, D, D, h->UW_stack + static_cast<size_t>(D) * D, D, 0, 0, s));
-    SRG_TRY(launch_pack_weight(p->W_p, D, D, D, h->UW_stack + 2 * static_cast<size_t>(D) * D, D, 0, 0, s));
+  auto pack_p = [&](int x, bf16* dst, int64_t row_off) -> int {  // x: 0 = h, 1 = z, 2 = r
+    for (int b = 0; b < split; ++b)
+      SRG_TRY(copy_block(dst, ld2, row_off, static_cast<int64_t>(b) * 2 * D, P_part[kPartB[b]] + x * DD, D, s));
+    return SRG_OK;
+  };
+  SRG_TRY(pack_p(1, h->Wzr, 0));
+  SRG_TRY(pack_u(p->U_z, D, D, h->Wzr, ld2, 0, 2 * D, D));
+  SRG_TRY(pack_p(2, h->Wzr, D));
+  SRG_TRY(pack_u(p->U_r, D, D, h->Wzr, ld2, D, 2 * D, D));
+  SRG_TRY(pack_p(0, h->Wh, 0));
+  SRG_TRY(pack_u(p->U_h, D, D, h->Wh, ld2, 0, 2 * D, D));
+  SRG_TRY(pack_u(p->Wc_noun, h->L, h->Lpad, h->Wcn, ld1, 0, D, 0));
+  SRG_TRY(pack_u(p->Wc_verb, h->V, h->Vpad, h->Wcv, ld1, 0, D, 0));
+  if (precision == SRG_PREC_BF16) {  // backward operands (MN-major B = stacks along K)
+    SRG_TRY(launch_pack_weight(p->U_z, D, D, D, h->U_stack, D, 0, 0, s));
+    SRG_TRY(launch_pack_weight(p->U_r, D, D, D, h->U_stack + DD, D, 0, 0, s));
     SRG_TRY(launch_pack_weight(p->U_h, D, D, D, h->Uh, D, 0, 0, s));
   }
-  SRG_TRY(launch_pack_bias(p->b_p, nullptr, D, D, h->bp, s));
-  SRG_TRY(launch_pack_bias(p->b_Wz, p->b_Uz, D, D, h->bzr, s));
-  SRG_TRY(launch_pack_bias(p->b_Wr, p->b_Ur, D, D, h->bzr + D, s));
-  SRG_TRY(launch_pack_bias(p->b_Wh, p->b_Uh, D, D, h->bh, s));
+
+  // (4) biases: b'_x(mode) = b_Wx + b_Ux + c W_x b_p, c = R for the noun graph (model.py:73-75: the projection bias is
+  //     added for all R neighbours before the sum), c = 1 for the verb node (model.py:62-64)
+  for (int x = 0; x < 3; ++x) SRG_TRY(launch_matvec(Wm32[x], p->b_p, D, D, h->wb + x * D, s));
+  for (int mi = 0; mi < 2; ++mi) {
+    const float c = (mi == 0) ? static_cast<float>(h->R) : 1.f;
+    SRG_TRY(launch_pack_bias3(p->b_Wz, p->b_Uz, h->wb + D, c, D, D, h->bzr[mi], s));
+    SRG_TRY(launch_pack_bias3(p->b_Wr, p->b_Ur, h->wb + 2 * D, c, D, D, h->bzr[mi] + D, s));
+    SRG_TRY(launch_pack_bias3(p->b_Wh, p->b_Uh, h->wb, c, D, D, h->bh[mi], s));
+  }
   SRG_TRY(launch_pack_bias(p->bc_noun, nullptr, h->L, h->Lpad, h->bcn, s));
   SRG_TRY(launch_pack_bias(p->bc_verb, nullptr, h->V, h->Vpad, h->bcv, s));
   h->packed_prec = precision;
@@ -579,7 +688,7 @@ int srg_nouns_forward(srg_handle* h, const float* feat, const int64_t* verb, int
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SRG_TRY(launch_gather_mask(h->d_verb2roles, h->d_role_count, h->V, h->R, verb, B, nullptr, pb.mask, nullptr, s));
   SRG_TRY(launch_node_init_noun(feat, role_emb, verb_emb, verb, h->d_verb2roles, h->V, B, h->R, h->D, pb.h32,
-                                pb.hb_hi[0], pb.hb_lo[0], s));
+                                pb.hb_hi[0], pb.hb_mid[0], pb.hb_lo[0], s));
   SRG_TRY(ggnn_steps(h, SRG_MODE_NOUN, pb, pb.h32, pb.mask, B, precision, save_for_backward, s));
   return classifier_forward(h, SRG_MODE_NOUN, pb, pb.h32, keep, drop_p, logits, ldl, precision, s);
 }
@@ -592,7 +701,7 @@ int srg_verb_forward(srg_handle* h, const float* feat, int B, const uint8_t* kee
   SRG_CHECK(h->packed_prec == precision, "srg_verb_forward: weights are not packed for precision %d", precision);
   SRG_CHECK(feat && logits, "srg_verb_forward: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  SRG_TRY(launch_node_init_verb(feat, B, h->D, pb.h32, pb.hb_hi[0], pb.hb_lo[0], s));
+  SRG_TRY(launch_node_init_verb(feat, B, h->D, pb.h32, pb.hb_hi[0], pb.hb_mid[0], pb.hb_lo[0], s));
   SRG_TRY(ggnn_steps(h, SRG_MODE_VERB, pb, pb.h32, nullptr, B, precision, save_for_backward, s));
   return classifier_forward(h, SRG_MODE_VERB, pb, pb.h32, keep, drop_p, logits, ldl, precision, s);
 }
@@ -606,7 +715,7 @@ int srg_ggnn_forward(srg_handle* h, int mode, float* hidden, const float* mask, 
   SRG_CHECK(hidden != nullptr, "null hidden state");
   SRG_CHECK(mode == SRG_MODE_VERB || mask != nullptr, "noun mode needs a mask");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  SRG_TRY(launch_split_cast(hidden, static_cast<int64_t>(pb.M) * h->D, pb.hb_hi[0], pb.hb_lo[0], s));
+  SRG_TRY(launch_split_cast(hidden, static_cast<int64_t>(pb.M) * h->D, pb.hb_hi[0], pb.hb_mid[0], pb.hb_lo[0], s));
   return ggnn_steps(h, mode, pb, hidden, mask, B, precision, save_for_backward, s);
 }
 

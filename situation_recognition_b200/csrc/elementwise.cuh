@@ -16,27 +16,28 @@ int launch_gather_mask(const int32_t* verb2roles, const int32_t* role_count, int
 // node[b*R+r, :] = relu(feat[b,:] * role_emb[verb2roles[verb[b], r], :] * verb_emb[verb[b], :])   (model.py:124-144)
 int launch_node_init_noun(const float* feat, const float* role_emb, const float* verb_emb, const int64_t* verb,
                           const int32_t* verb2roles, int n_verbs, int B, int R, int D, float* h32, bf16* hb_hi,
-                          bf16* hb_lo, cudaStream_t s);
+                          bf16* hb_mid, bf16* hb_lo, cudaStream_t s);
 // node = relu(feat)  (model.py:160)
-int launch_node_init_verb(const float* feat, int B, int D, float* h32, bf16* hb_hi, bf16* hb_lo, cudaStream_t s);
-// fp32 -> bf16 hi (+lo)
-int launch_split_cast(const float* x, int64_t n, bf16* hi, bf16* lo, cudaStream_t s);
+int launch_node_init_verb(const float* feat, int B, int D, float* h32, bf16* hb_hi, bf16* hb_mid, bf16* hb_lo,
+                          cudaStream_t s);
+// fp32 -> bf16 hi (+ mid, lo residual parts when non-null)
+int launch_split_cast(const float* x, int64_t n, bf16* hi, bf16* mid, bf16* lo, cudaStream_t s);
 
 // a[b,i,:] = sum_j mask[b,i,j] * h[b,j,:]    (model.py:67-75 with the projection hoisted out of the sum)
-int launch_aggregate(const float* h32, const float* mask, int B, int R, int D, bf16* a_hi, bf16* a_lo,
+int launch_aggregate(const float* h32, const float* mask, int B, int R, int D, bf16* a_hi, bf16* a_mid, bf16* a_lo,
                      cudaStream_t s);
 // dh[b,j,:] = dh_acc[b,j,:] + sum_i mask[b,i,j] * da[b,i,:]
 int launch_aggregate_bwd(const float* dh_acc, const float* da, const float* mask, int B, int R, int D, float* dh,
                          cudaStream_t s);
 
-// dst[r, col_off + c] = hi/lo bf16 part of src[r, c] (r < rows), 0 for rows <= r < rows_pad
+// dst[r, col_off + c] = bf16 part `want_lo` (0 hi, 1 mid, 2 lo) of src[r, c] (r < rows), 0 for rows <= r < rows_pad
 int launch_pack_weight(const float* src, int rows, int cols, int rows_pad, bf16* dst, int64_t ld_dst, int64_t col_off,
                        int want_lo, cudaStream_t s);
 // dst[i] = a[i] (+ b[i]) for i < n, 0 for n <= i < n_pad
 int launch_pack_bias(const float* a, const float* b, int n, int n_pad, float* dst, cudaStream_t s);
 
 // x = h * keep / (1-p)  -> bf16 hi (+lo)
-int launch_dropout_cast(const float* h32, const uint8_t* keep, float scale, int64_t n, bf16* hi, bf16* lo,
+int launch_dropout_cast(const float* h32, const uint8_t* keep, float scale, int64_t n, bf16* hi, bf16* mid, bf16* lo,
                         cudaStream_t s);
 // dh = dx * keep / (1-p)   (keep may be null)
 int launch_dropout_bwd(const float* dx, const uint8_t* keep, float scale, int64_t n, float* dh, cudaStream_t s);
@@ -63,15 +64,30 @@ int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, c
 
 // adm[b,j,:] = sum_i mask[b,i,j] * dm[b,i,:]   (bf16 in / bf16 out; the aggregation commutes with the W_p GEMM)
 int launch_aggregate_t_bf16(const bf16* dm, const float* mask, int B, int R, int D, bf16* adm, cudaStream_t s);
-// up to 4 column sums in one launch
+// up to 4 column sums in one launch: out1/out2 += scale * colsum, out3 += scale3 * colsum
 struct ColsumJob {
   const bf16* X;
   float* out1;
   float* out2;
   float scale;
+  float* out3;
+  float scale3;
 };
 int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows, int n_cols, cudaStream_t s);
 
 int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s);
+
+// GRU backward prologue writing into column blocks of a wider matrix (leading dimension ld_out elements)
+int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int rows, int D,
+                          bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc, cudaStream_t s);
+// y[o] = sum_k W[o,k] x[k]                       (fp32, W row-major [rows, cols])
+int launch_matvec(const float* W, const float* x, int rows, int cols, float* y, cudaStream_t s);
+// y[k] += sum_o W[o,k] s[o]
+int launch_matvec_t_acc(const float* W, const float* sv, int rows, int cols, float* y, cudaStream_t s);
+// dW[o,k] += s[o] * b[k]
+int launch_outer_acc(const float* sv, const float* b, int rows, int cols, float* dW, cudaStream_t s);
+// dst[i] = a[i] + b[i] + scale * c[i]   (b, c nullable; zero beyond n up to n_pad)
+int launch_pack_bias3(const float* a, const float* b, const float* c, float scale, int n, int n_pad, float* dst,
+                      cudaStream_t s);
 
 }  // namespace srg

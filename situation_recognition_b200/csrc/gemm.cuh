@@ -25,12 +25,12 @@ constexpr int kTileM = 128;     // rows per CTA
 constexpr int kNumThreads = 256;
 constexpr int kEpiWarp0 = 4;
 constexpr int kSlotBytes = 4096;  // 32 rows x 128 B
-constexpr int kMaxSeg = 8;
-constexpr int kMaxAMaps = 4;
+constexpr int kMaxSeg = 12;
+constexpr int kMaxAMaps = 6;
 constexpr int kMaxIoMaps = 7;
 
 enum EpiKind : int {
-  EPI_STORE_BF16 = 0,  // io0 = out hi (bf16), io1 = out lo (bf16, FLAG_LO)
+  EPI_STORE_BF16 = 0,  // io0 = out hi (bf16); FLAG_LO: io1 = mid, io2 = lo  (3-way bf16 split x = hi + mid + lo)
   EPI_STORE_F32 = 1,   // io0 = out fp32 (FLAG_REDUCE: += via TMA reduce-add)
   EPI_ZR = 2,          // GRU update/reset gates:  z = sig(.), r = sig(.), rh = r*h
   EPI_H = 3,           // GRU candidate + state update: hc = tanh(.), h' = h + z*(hc - h)
@@ -54,6 +54,7 @@ struct GemmArgs {
   int seg_acol[kMaxSeg];  // start coordinate along K inside the A map (elements)
   int seg_kb[kMaxSeg];    // k-blocks in this segment
   int total_kb;
+  int corr_kb_begin;  // F32 instantiations: k-blocks >= this accumulate into the correction accumulator
   int k_splits;
   float alpha;
   const float* bias;  // [N] or nullptr
@@ -66,10 +67,10 @@ struct GemmArgs {
 
 template <int EPI, bool F32>
 struct EpiTraits {
-  static constexpr int kSlots = (EPI == EPI_STORE_BF16) ? 4
+  static constexpr int kSlots = (EPI == EPI_STORE_BF16) ? (F32 ? 6 : 2)
                                 : (EPI == EPI_STORE_F32) ? 4
                                 : (EPI == EPI_ZR)        ? (F32 ? 6 : 5)
-                                : (EPI == EPI_H)         ? (F32 ? 6 : 4)
+                                : (EPI == EPI_H)         ? (F32 ? 7 : 4)
                                 : (EPI == EPI_LOGITS)    ? 4
                                 : (EPI == EPI_DH)        ? 6
                                                          : 6;
@@ -155,19 +156,23 @@ __device__ __forceinline__ void slot_st_bf16x8(uint32_t slot, int lane, int c, c
   sts128(slot_addr(slot, lane, c), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
          pack_bf16(v[6], v[7]));
 }
-// hi/lo split store: hi = bf16(v), lo = bf16(v - hi)
-__device__ __forceinline__ void slot_st_bf16x8_split(uint32_t slot_hi, uint32_t slot_lo, int lane, int c,
-                                                     const float (&v)[8]) {
-  uint32_t hi[4];
-  float lo[8];
+// 3-way split store: hi = bf16(v), mid = bf16(v - hi), lo = bf16(v - hi - mid)  (24 significant bits in total)
+__device__ __forceinline__ void slot_st_bf16x8_split(uint32_t slot_hi, uint32_t slot_mid, uint32_t slot_lo, int lane,
+                                                     int c, const float (&v)[8]) {
+  uint32_t hi[4], mid[4];
+  float r1[8], r2[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     hi[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-    lo[2 * i] = v[2 * i] - bf16_lo_f(hi[i]);
-    lo[2 * i + 1] = v[2 * i + 1] - bf16_hi_f(hi[i]);
+    r1[2 * i] = v[2 * i] - bf16_lo_f(hi[i]);
+    r1[2 * i + 1] = v[2 * i + 1] - bf16_hi_f(hi[i]);
+    mid[i] = pack_bf16(r1[2 * i], r1[2 * i + 1]);
+    r2[2 * i] = r1[2 * i] - bf16_lo_f(mid[i]);
+    r2[2 * i + 1] = r1[2 * i + 1] - bf16_hi_f(mid[i]);
   }
   sts128(slot_addr(slot_hi, lane, c), hi[0], hi[1], hi[2], hi[3]);
-  slot_st_bf16x8(slot_lo, lane, c, lo);
+  sts128(slot_addr(slot_mid, lane, c), mid[0], mid[1], mid[2], mid[3]);
+  slot_st_bf16x8(slot_lo, lane, c, r2);
 }
 
 __device__ __forceinline__ void load_bias8(const float* bias, int col, float scale, float (&b)[8]) {
@@ -331,12 +336,19 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
         const int ks = w / tiles_mn;
         const int kb_begin = ks * kb_per_split;
         const int kb_end = min(args.total_kb, kb_begin + kb_per_split);
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
+        // F32 (parity) instantiations use the two TMEM accumulators of ONE tile: the leading hi*hi terms go to the
+        // first, the small split-correction terms to the second (they are summed in fp32 in the epilogue).  The tensor
+        // core truncates when it adds into the accumulator, so keeping the ~2^-9-sized corrections out of the large
+        // running sum keeps that bias proportional to K/16 and not to 6K/16.
+        const int acc = F32 ? 0 : (iter & 1);
+        const uint32_t acc_phase = F32 ? (iter & 1) : ((iter >> 1) & 1);
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         ptx::tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_main = tmem_base + acc * BLOCK_N;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const bool corr = F32 && kb >= args.corr_kb_begin;
+          const uint32_t tmem_d = corr ? tmem_base + BLOCK_N : tmem_main;
+          const int first_kb = corr ? args.corr_kb_begin : kb_begin;
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tcgen05_fence_after();
           const uint32_t sa = ptx::smem_u32(smem_a + stage * A_BYTES);
@@ -345,7 +357,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t da = ptx::make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
             const uint64_t db = ptx::make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
-            ptx::umma_bf16<CG>(tmem_d, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            ptx::umma_bf16<CG>(tmem_d, da, db, idesc, (kb > first_kb || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit<CG>(&empty_bar[stage]);  // frees this smem stage (both CTAs) when the MMAs retire
           if (kb == kb_end - 1) ptx::umma_commit<CG>(&tmem_full_bar[acc]);
@@ -371,13 +383,28 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
       const int mt = (w % tiles_mn) / num_n_tiles;
       const int row0 = mt * kTileM * CG + static_cast<int>(cta_rank) * kTileM + ew * 32;  // first row of this warp
       const int n0 = nt * BLOCK_N;
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int acc = F32 ? 0 : (iter & 1);
+      const uint32_t acc_phase = F32 ? (iter & 1) : ((iter >> 1) & 1);
       const bool warp_active = row0 < args.M;  // TMA clips partially valid boxes itself
 
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+      const bool has_corr = F32 && args.corr_kb_begin < args.total_kb;
+      // 32 accumulator columns of this lane's row (main + correction accumulator in the parity instantiations)
+      auto load_acc = [&](int col, float (&v)[32]) {
+        ptx::tmem_ld_32x32(tacc + col, v);
+        ptx::tmem_ld_wait();
+        if constexpr (F32) {
+          if (has_corr) {
+            float c2[32];
+            ptx::tmem_ld_32x32(tacc + BLOCK_N + col, c2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += c2[i];
+          }
+        }
+      };
 
       // per-row softmax statistics (EPI_LOGITS)
       float st_max = -INFINITY, st_sum = 0.f;
@@ -389,20 +416,20 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
         float accv[32];
 
         if constexpr (EPI == EPI_STORE_BF16) {
-          const int s_hi = store_set * 2, s_lo = store_set * 2 + 1;
+          constexpr int kPer = F32 ? 3 : 1;   // the 3-way split output exists only in the F32 instantiation
+          const int s_hi = store_set * kPer, s_mid = s_hi + (F32 ? 1 : 0), s_lo = s_hi + (F32 ? 2 : 0);
           if (lane == 0) ptx::tma_wait_group_read<1>();
           __syncwarp();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            ptx::tmem_ld_32x32(tacc + cc * 64 + half * 32, accv);
-            ptx::tmem_ld_wait();
+            load_acc(cc * 64 + half * 32, accv);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float b[8], v[8];
               load_bias8(args.bias, gcol + half * 32 + g * 8, args.bias_scale, b);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = fmaf(accv[g * 8 + i], args.alpha, b[i]);
-              if (args.flags & FLAG_LO) slot_st_bf16x8_split(slot(s_hi), slot(s_lo), lane, half * 4 + g, v);
+              if (F32 && (args.flags & FLAG_LO)) slot_st_bf16x8_split(slot(s_hi), slot(s_mid), slot(s_lo), lane, half * 4 + g, v);
               else slot_st_bf16x8(slot(s_hi), lane, half * 4 + g, v);
             }
           }
@@ -411,7 +438,10 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
           if (lane == 0) {
             if (warp_active) {
               ptx::tma_store_2d(&maps.io[0], slot_ptr(s_hi), gcol, row0);
-              if (args.flags & FLAG_LO) ptx::tma_store_2d(&maps.io[1], slot_ptr(s_lo), gcol, row0);
+              if (F32 && (args.flags & FLAG_LO)) {
+                ptx::tma_store_2d(&maps.io[1], slot_ptr(s_mid), gcol, row0);
+                ptx::tma_store_2d(&maps.io[2], slot_ptr(s_lo), gcol, row0);
+              }
             }
             ptx::tma_commit_group();
           }
@@ -422,8 +452,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
           __syncwarp();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            ptx::tmem_ld_32x32(tacc + cc * 64 + half * 32, accv);
-            ptx::tmem_ld_wait();
+            load_acc(cc * 64 + half * 32, accv);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float b[8], v[8];
@@ -454,8 +483,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
           __syncwarp();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            ptx::tmem_ld_32x32(tacc + cc * 64 + half * 32, accv);
-            ptx::tmem_ld_wait();
+            load_acc(cc * 64 + half * 32, accv);
             float hmax = -INFINITY;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -496,8 +524,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
             __syncwarp();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              ptx::tmem_ld_32x32(tacc + cc * 64 + half * 32, accv);
-              ptx::tmem_ld_wait();
+              load_acc(cc * 64 + half * 32, accv);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 float b[8], v[8];
@@ -522,7 +549,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
               ptx::tma_commit_group();
             }
           } else {
-            // ---- reset gate r = sigmoid(acc + b); rh = r * h.  in: io1 = h (fp32); out: io2 = rh hi, io3 = rh lo,
+            // ---- reset gate r = sigmoid(acc + b); rh = r * h.  in: io1 = h (fp32); out: io2 = rh hi, io3/io5 = rh mid/lo,
             //      io4 = r (bf16 stash for the backward pass)
             const int hcol = gcol - args.n_split;
             if (lane == 0) {
@@ -535,8 +562,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
             in_phase ^= 1u;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              ptx::tmem_ld_32x32(tacc + cc * 64 + half * 32, accv);
-              ptx::tmem_ld_wait();
+              load_acc(cc * 64 + half * 32, accv);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 float b[8], r[8], h[8], rh[8];
@@ -547,7 +573,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
                   r[i] = act_sigmoid<F32>(accv[g * 8 + i] + b[i]);
                   rh[i] = r[i] * h[i];
                 }
-                if (args.flags & FLAG_LO) slot_st_bf16x8_split(slot(2), slot(3), lane, half * 4 + g, rh);
+                if (args.flags & FLAG_LO) slot_st_bf16x8_split(slot(2), slot(3), slot(5), lane, half * 4 + g, rh);
                 else slot_st_bf16x8(slot(2), lane, half * 4 + g, rh);
                 if (args.flags & FLAG_STASH) slot_st_bf16x8(slot(4), lane, half * 4 + g, r);
               }
@@ -557,7 +583,10 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
             if (lane == 0) {
               if (warp_active) {
                 ptx::tma_store_2d(&maps.io[2], slot_ptr(2), hcol, row0);
-                if (args.flags & FLAG_LO) ptx::tma_store_2d(&maps.io[3], slot_ptr(3), hcol, row0);
+                if (args.flags & FLAG_LO) {
+                  ptx::tma_store_2d(&maps.io[3], slot_ptr(3), hcol, row0);
+                  ptx::tma_store_2d(&maps.io[5], slot_ptr(5), hcol, row0);
+                }
                 if (args.flags & FLAG_STASH) ptx::tma_store_2d(&maps.io[4], slot_ptr(4), hcol, row0);
               }
               ptx::tma_commit_group();
@@ -566,8 +595,8 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
         } else if constexpr (EPI == EPI_H) {
           // hc = tanh(acc + b); h' = h + z * (hc - h)
           // io0 = h fp32 (read, then overwritten in place with h'), io1 = z (bf16 | fp32 in F32 mode),
-          // io2 = h' hi (bf16), io3 = h' lo (F32 mode), io4 = hc (bf16 stash)
-          constexpr int S_H = 0, S_Z = 2, S_HB = F32 ? 4 : 3, S_HL = 5;
+          // io2 = h' hi (bf16), io3 / io5 = h' mid / lo (F32 mode), io4 = hc (bf16 stash)
+          constexpr int S_H = 0, S_Z = 2, S_HB = F32 ? 4 : 3, S_HM = 5, S_HL = 6;
           if (lane == 0) {
             ptx::tma_wait_group_read<0>();
             ptx::mbar_arrive_expect_tx(in_bar, (F32 ? 4 : 3) * kSlotBytes);
@@ -580,8 +609,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
           in_phase ^= 1u;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            ptx::tmem_ld_32x32(tacc + cc * 64 + half * 32, accv);
-            ptx::tmem_ld_wait();
+            load_acc(cc * 64 + half * 32, accv);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float b[8], h[8], z[8], hc[8], hn[8];
@@ -596,7 +624,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
               }
               slot_st_f32x8(slot(S_H + half), lane, g, hn);
               if constexpr (F32) {
-                slot_st_bf16x8_split(slot(S_HB), slot(S_HL), lane, half * 4 + g, hn);
+                slot_st_bf16x8_split(slot(S_HB), slot(S_HM), slot(S_HL), lane, half * 4 + g, hn);
               } else {
                 slot_st_bf16x8(slot(S_HB), lane, half * 4 + g, hn);
                 if (args.flags & FLAG_STASH) slot_st_bf16x8(slot(S_Z), lane, half * 4 + g, hc);
@@ -610,7 +638,10 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
               ptx::tma_store_2d(&maps.io[0], slot_ptr(S_H), gcol, row0);
               ptx::tma_store_2d(&maps.io[0], slot_ptr(S_H + 1), gcol + 32, row0);
               ptx::tma_store_2d(&maps.io[2], slot_ptr(S_HB), gcol, row0);
-              if constexpr (F32) ptx::tma_store_2d(&maps.io[3], slot_ptr(S_HL), gcol, row0);
+              if constexpr (F32) {
+                ptx::tma_store_2d(&maps.io[3], slot_ptr(S_HM), gcol, row0);
+                ptx::tma_store_2d(&maps.io[5], slot_ptr(S_HL), gcol, row0);
+              }
               else if (args.flags & FLAG_STASH) ptx::tma_store_2d(&maps.io[4], slot_ptr(S_Z), gcol, row0);
             }
             ptx::tma_commit_group();
@@ -632,8 +663,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
           in_phase ^= 1u;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            ptx::tmem_ld_32x32(tacc + cc * 64 + half * 32, accv);
-            ptx::tmem_ld_wait();
+            load_acc(cc * 64 + half * 32, accv);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float h[8], r[8], dh[8], dp[8];
@@ -686,8 +716,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
           in_phase ^= 1u;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            ptx::tmem_ld_32x32(tacc + cc * 64 + half * 32, accv);
-            ptx::tmem_ld_wait();
+            load_acc(cc * 64 + half * 32, accv);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float dh[8];

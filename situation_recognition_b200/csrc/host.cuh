@@ -146,6 +146,7 @@ struct GemmProblem {
   float* stats = nullptr;
   int flags = 0;
   int k_splits = 1;
+  int corr_seg_begin = -1;  // first A segment of the split-correction terms (fp32-parity problems), -1 = none
   int max_clusters = 0;  // 0 = all SMs
 };
 
@@ -218,7 +219,9 @@ inline int dispatch_gemm(const GemmProblem& p, const GemmMaps& maps, const GemmA
   SRG_CASE(false, false, EPI_H, false)
   SRG_CASE(false, false, EPI_H, true)
   SRG_CASE(false, false, EPI_LOGITS, false)
+  SRG_CASE(false, false, EPI_LOGITS, true)
   SRG_CASE(false, true, EPI_STORE_BF16, false)
+  SRG_CASE(false, true, EPI_STORE_BF16, true)
   SRG_CASE(false, true, EPI_STORE_F32, false)
   SRG_CASE(false, true, EPI_DRH, false)
   SRG_CASE(false, true, EPI_DH, false)
@@ -253,6 +256,7 @@ inline int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t st
   const void* aptr[kMaxAMaps];
   int n_amaps = 0;
   int ktot = 0;
+  args.corr_kb_begin = 1 << 30;
   for (int s = 0; s < p.nseg; ++s) {
     const GemmSeg& sg = p.seg[s];
     // a K tail (< 64) is legal only in the last segment: TMA zero-fills beyond the tensor extent of A and B
@@ -277,6 +281,7 @@ inline int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t st
     const int64_t kext = p.a_mn ? sg.a.rows : sg.a.cols;
     SRG_CHECK(sg.k_off >= 0 && sg.k_off + sg.k_len <= kext, "gemm: segment %d K range [%d,%d) outside A (%lld)", s,
               sg.k_off, sg.k_off + sg.k_len, (long long)kext);
+    if (s == p.corr_seg_begin) args.corr_kb_begin = ktot / kBlockK;
     args.seg_map[s] = mi;
     args.seg_acol[s] = sg.k_off;
     args.seg_kb[s] = (sg.k_len + kBlockK - 1) / kBlockK;

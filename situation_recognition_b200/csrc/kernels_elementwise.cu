@@ -25,12 +25,20 @@ __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) 
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// store 4 values as bf16 hi (and the residual as bf16 lo when lo != nullptr)
-__device__ __forceinline__ void store4_split(bf16* hi, bf16* lo, int64_t idx, float4 v) {
+// bf16 operand parts of 4 values: hi = bf16(v); when `parts` carries the residual pointers also
+// mid = bf16(v - hi) and lo = bf16(v - hi - mid)  (fp32-parity mode: x = hi + mid + lo to 24 bits)
+struct Parts {
+  bf16* mid;
+  bf16* lo;
+};
+__device__ __forceinline__ void store4_split(bf16* hi, Parts parts, int64_t idx, float4 v) {
   *reinterpret_cast<uint2*>(hi + idx) = pack4_bf16(v.x, v.y, v.z, v.w);
-  if (lo != nullptr) {
-    *reinterpret_cast<uint2*>(lo + idx) =
-        pack4_bf16(v.x - bf16_round(v.x), v.y - bf16_round(v.y), v.z - bf16_round(v.z), v.w - bf16_round(v.w));
+  if (parts.mid != nullptr) {
+    const float4 r1 = make_float4(v.x - bf16_round(v.x), v.y - bf16_round(v.y), v.z - bf16_round(v.z),
+                                  v.w - bf16_round(v.w));
+    *reinterpret_cast<uint2*>(parts.mid + idx) = pack4_bf16(r1.x, r1.y, r1.z, r1.w);
+    *reinterpret_cast<uint2*>(parts.lo + idx) = pack4_bf16(r1.x - bf16_round(r1.x), r1.y - bf16_round(r1.y),
+                                                           r1.z - bf16_round(r1.z), r1.w - bf16_round(r1.w));
   }
 }
 
@@ -63,7 +71,7 @@ __global__ void k_gather_mask(const int32_t* __restrict__ verb2roles, const int3
 __global__ void k_node_init_noun(const float* __restrict__ feat, const float* __restrict__ role_emb,
                                  const float* __restrict__ verb_emb, const int64_t* __restrict__ verb,
                                  const int32_t* __restrict__ verb2roles, int n_verbs, int B, int R, int D,
-                                 float* __restrict__ h32, bf16* __restrict__ hb_hi, bf16* __restrict__ hb_lo) {
+                                 float* __restrict__ h32, bf16* __restrict__ hb_hi, Parts hb_lo) {
   const int D4 = D / 4;
   const int64_t total = static_cast<int64_t>(B) * D4;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
@@ -91,7 +99,7 @@ __global__ void k_node_init_noun(const float* __restrict__ feat, const float* __
 }
 
 __global__ void k_node_init_verb(const float* __restrict__ feat, int64_t n4, float* __restrict__ h32,
-                                 bf16* __restrict__ hb_hi, bf16* __restrict__ hb_lo) {
+                                 bf16* __restrict__ hb_hi, Parts hb_lo) {
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 f = *reinterpret_cast<const float4*>(feat + t * 4);
@@ -101,7 +109,7 @@ __global__ void k_node_init_verb(const float* __restrict__ feat, int64_t n4, flo
   }
 }
 
-__global__ void k_split_cast(const float* __restrict__ x, int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+__global__ void k_split_cast(const float* __restrict__ x, int64_t n4, bf16* __restrict__ hi, Parts lo) {
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float4 f = *reinterpret_cast<const float4*>(x + t * 4);
@@ -111,7 +119,7 @@ __global__ void k_split_cast(const float* __restrict__ x, int64_t n4, bf16* __re
 
 // ------------------------------------------------------------------------------------------------ aggregation
 __global__ void k_aggregate(const float* __restrict__ h32, const float* __restrict__ mask, int B, int R, int D,
-                            bf16* __restrict__ a_hi, bf16* __restrict__ a_lo) {
+                            bf16* __restrict__ a_hi, Parts a_lo) {
   const int D4 = D / 4;
   const int64_t total = static_cast<int64_t>(B) * D4;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
@@ -184,7 +192,7 @@ __global__ void k_pack_weight(const float* __restrict__ src, int rows, int cols,
     const int c = static_cast<int>(t % c2) * 2;
     float2 v = make_float2(0.f, 0.f);
     if (r < rows) v = *reinterpret_cast<const float2*>(src + static_cast<int64_t>(r) * cols + c);
-    if (want_lo) {
+    for (int k = 0; k < want_lo; ++k) {   // want_lo = 0: hi part, 1: mid residual, 2: lo residual
       v.x -= bf16_round(v.x);
       v.y -= bf16_round(v.y);
     }
@@ -204,7 +212,7 @@ __global__ void k_pack_bias(const float* __restrict__ a, const float* __restrict
 
 // ------------------------------------------------------------------------------------------------ dropout
 __global__ void k_dropout_cast(const float* __restrict__ h32, const uint8_t* __restrict__ keep, float scale,
-                               int64_t n4, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+                               int64_t n4, bf16* __restrict__ hi, Parts lo) {
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 f = *reinterpret_cast<const float4*>(h32 + t * 4);
@@ -538,6 +546,84 @@ __global__ void k_colsum_multi(ColsumJobs jobs, int64_t ld, int rows, int n_cols
       atomicAdd(job.out2 + c, t.x * job.scale);
       if (c + 1 < n_cols) atomicAdd(job.out2 + c + 1, t.y * job.scale);
     }
+    if (job.out3 != nullptr) {
+      atomicAdd(job.out3 + c, t.x * job.scale3);
+      if (c + 1 < n_cols) atomicAdd(job.out3 + c + 1, t.y * job.scale3);
+    }
+  }
+}
+
+__global__ void k_gru_bwd_pre_ld(const float* __restrict__ dh, const bf16* __restrict__ z, const bf16* __restrict__ hc,
+                                 const bf16* __restrict__ h, int rows, int D, bf16* __restrict__ dpre_z,
+                                 bf16* __restrict__ dpre_h, int64_t ld_out, float* __restrict__ dh_acc) {
+  const int D4 = D / 4;
+  const int64_t total = static_cast<int64_t>(rows) * D4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = t / D4;
+    const int col = static_cast<int>(t % D4) * 4;
+    const int64_t i = row * D + col;
+    const float4 g = *reinterpret_cast<const float4*>(dh + i);
+    const uint2 zz = *reinterpret_cast<const uint2*>(z + i);
+    const uint2 cc = *reinterpret_cast<const uint2*>(hc + i);
+    const uint2 hh = *reinterpret_cast<const uint2*>(h + i);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+    const float zv[4] = {bf16_lo_f(zz.x), bf16_hi_f(zz.x), bf16_lo_f(zz.y), bf16_hi_f(zz.y)};
+    const float cv[4] = {bf16_lo_f(cc.x), bf16_hi_f(cc.x), bf16_lo_f(cc.y), bf16_hi_f(cc.y)};
+    const float hv[4] = {bf16_lo_f(hh.x), bf16_hi_f(hh.x), bf16_lo_f(hh.y), bf16_hi_f(hh.y)};
+    float dz[4], dc[4], da[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      dz[k] = gv[k] * (cv[k] - hv[k]) * zv[k] * (1.f - zv[k]);
+      dc[k] = gv[k] * zv[k] * (1.f - cv[k] * cv[k]);
+      da[k] = gv[k] * (1.f - zv[k]);
+    }
+    *reinterpret_cast<uint2*>(dpre_z + row * ld_out + col) = pack4_bf16(dz[0], dz[1], dz[2], dz[3]);
+    *reinterpret_cast<uint2*>(dpre_h + row * ld_out + col) = pack4_bf16(dc[0], dc[1], dc[2], dc[3]);
+    *reinterpret_cast<float4*>(dh_acc + i) = make_float4(da[0], da[1], da[2], da[3]);
+  }
+}
+
+// one warp per output row
+__global__ void k_matvec(const float* __restrict__ W, const float* __restrict__ x, int rows, int cols,
+                         float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float acc = 0.f;
+  for (int k = lane; k < cols; k += 32) acc = fmaf(W[static_cast<int64_t>(row) * cols + k], x[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[row] = acc;
+}
+
+// grid = (cols / 256, row slabs); y[k] += sum over the slab of W[o,k] s[o]
+__global__ void k_matvec_t_acc(const float* __restrict__ W, const float* __restrict__ sv, int rows, int cols,
+                               float* __restrict__ y) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  if (k >= cols) return;
+  float acc = 0.f;
+  for (int o = r0; o < r1; ++o) acc = fmaf(W[static_cast<int64_t>(o) * cols + k], sv[o], acc);
+  atomicAdd(y + k, acc);
+}
+
+__global__ void k_outer_acc(const float* __restrict__ sv, const float* __restrict__ b, int rows, int cols,
+                            float* __restrict__ dW) {
+  const int64_t total = static_cast<int64_t>(rows) * cols;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(t / cols), k = static_cast<int>(t % cols);
+    dW[t] += sv[o] * b[k];
+  }
+}
+
+__global__ void k_pack_bias3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                             float scale, int n, int n_pad, float* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < n) v = a[i] + (b != nullptr ? b[i] : 0.f) + (c != nullptr ? scale * c[i] : 0.f);
+    dst[i] = v;
   }
 }
 
@@ -569,34 +655,36 @@ int launch_gather_mask(const int32_t* verb2roles, const int32_t* role_count, int
 
 int launch_node_init_noun(const float* feat, const float* role_emb, const float* verb_emb, const int64_t* verb,
                           const int32_t* verb2roles, int n_verbs, int B, int R, int D, float* h32, bf16* hb_hi,
-                          bf16* hb_lo, cudaStream_t s) {
+                          bf16* hb_mid, bf16* hb_lo, cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   k_node_init_noun<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(
-      feat, role_emb, verb_emb, verb, verb2roles, n_verbs, B, R, D, h32, hb_hi, hb_lo);
+      feat, role_emb, verb_emb, verb, verb2roles, n_verbs, B, R, D, h32, hb_hi, Parts{hb_mid, hb_lo});
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
-int launch_node_init_verb(const float* feat, int B, int D, float* h32, bf16* hb_hi, bf16* hb_lo, cudaStream_t s) {
+int launch_node_init_verb(const float* feat, int B, int D, float* h32, bf16* hb_hi, bf16* hb_mid, bf16* hb_lo,
+                          cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   const int64_t n4 = static_cast<int64_t>(B) * D / 4;
-  k_node_init_verb<<<grid_for(n4), kThreads, 0, s>>>(feat, n4, h32, hb_hi, hb_lo);
+  k_node_init_verb<<<grid_for(n4), kThreads, 0, s>>>(feat, n4, h32, hb_hi, Parts{hb_mid, hb_lo});
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
-int launch_split_cast(const float* x, int64_t n, bf16* hi, bf16* lo, cudaStream_t s) {
+int launch_split_cast(const float* x, int64_t n, bf16* hi, bf16* mid, bf16* lo, cudaStream_t s) {
   if (n <= 0) return SRG_OK;
-  k_split_cast<<<grid_for(n / 4), kThreads, 0, s>>>(x, n / 4, hi, lo);
+  k_split_cast<<<grid_for(n / 4), kThreads, 0, s>>>(x, n / 4, hi, Parts{mid, lo});
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
-int launch_aggregate(const float* h32, const float* mask, int B, int R, int D, bf16* a_hi, bf16* a_lo,
+int launch_aggregate(const float* h32, const float* mask, int B, int R, int D, bf16* a_hi, bf16* a_mid, bf16* a_lo,
                      cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
-  k_aggregate<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(h32, mask, B, R, D, a_hi, a_lo);
+  k_aggregate<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(h32, mask, B, R, D, a_hi,
+                                                                             Parts{a_mid, a_lo});
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
@@ -624,10 +712,10 @@ int launch_pack_bias(const float* a, const float* b, int n, int n_pad, float* ds
   return SRG_OK;
 }
 
-int launch_dropout_cast(const float* h32, const uint8_t* keep, float scale, int64_t n, bf16* hi, bf16* lo,
+int launch_dropout_cast(const float* h32, const uint8_t* keep, float scale, int64_t n, bf16* hi, bf16* mid, bf16* lo,
                         cudaStream_t s) {
   if (n <= 0) return SRG_OK;
-  k_dropout_cast<<<grid_for(n / 4), kThreads, 0, s>>>(h32, keep, scale, n / 4, hi, lo);
+  k_dropout_cast<<<grid_for(n / 4), kThreads, 0, s>>>(h32, keep, scale, n / 4, hi, Parts{mid, lo});
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
@@ -724,6 +812,41 @@ int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows,
   if (slabs > 37) slabs = 37;
   dim3 grid((n_cols + 63) / 64, slabs, n_jobs);
   k_colsum_multi<<<grid, kThreads, 0, s>>>(js, ld, rows, n_cols);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int rows, int D,
+                          bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc, cudaStream_t s) {
+  if (rows <= 0) return SRG_OK;
+  k_gru_bwd_pre_ld<<<grid_for(static_cast<int64_t>(rows) * D / 4), kThreads, 0, s>>>(dh, z, hc, h, rows, D, dpre_z,
+                                                                                    dpre_h, ld_out, dh_acc);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_matvec(const float* W, const float* x, int rows, int cols, float* y, cudaStream_t s) {
+  k_matvec<<<(rows + 7) / 8, kThreads, 0, s>>>(W, x, rows, cols, y);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_matvec_t_acc(const float* W, const float* sv, int rows, int cols, float* y, cudaStream_t s) {
+  dim3 grid((cols + kThreads - 1) / kThreads, 32);
+  k_matvec_t_acc<<<grid, kThreads, 0, s>>>(W, sv, rows, cols, y);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_outer_acc(const float* sv, const float* b, int rows, int cols, float* dW, cudaStream_t s) {
+  k_outer_acc<<<grid_for(static_cast<int64_t>(rows) * cols), kThreads, 0, s>>>(sv, b, rows, cols, dW);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_pack_bias3(const float* a, const float* b, const float* c, float scale, int n, int n_pad, float* dst,
+                      cudaStream_t s) {
+  k_pack_bias3<<<grid_for(n_pad), kThreads, 0, s>>>(a, b, c, scale, n, n_pad, dst);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
