@@ -23,6 +23,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_IMAGE_FWD_BWD = 6.547e9   # BASELINE.md section 3 (algorithmic, aggregate-then-project)
+# dram__bytes_read.sum + dram__bytes_write.sum of one noun-path launch (M = 36864) from the `ncu --set full` captures
+# summarised under profiles/ (r01_ncu_full_gru_kernels.md); None = not captured yet
+NCU_TRAFFIC_BYTES = {"gemm_gru_zr_ab": 1.135e9 + 0.435e9, "gemm_gru_h_ab": 0.982e9 + 0.560e9}
 METRIC = "ggnn_images_per_sec_fwd_bwd"
 UNIT = "images/s"
 D = 2048
@@ -191,8 +194,8 @@ def run_ours(args):
     if args.cta_group:
         model._engine_for(dev).set_cta_group(args.cta_group)
     flat = parallel.attach(model)
-    # CUDA-graph replay on one GPU; with NCCL in the step the kernels are launched eagerly (--graph forces capture)
-    use_graph = (not args.no_graph) and (world == 1 or args.graph)
+    # the whole step (NCCL all-reduce included) is replayed from one CUDA graph; --no-graph launches eagerly
+    use_graph = not args.no_graph
     opt = torch.optim.Adamax(model.parameters(), lr=0.002, capturable=use_graph)      # sr.py:472-473
     params = [p for p in model.parameters() if p.requires_grad]
 
@@ -279,12 +282,15 @@ def run_ours(args):
     gemm_ms = sum(d["ms_per_step"] for d in per_kind)
     executed_flops_per_step = sum(fl_k[k] for k in range(kinds)) / args.steps * world   # all ranks
     roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": peaks["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": top["tflops"] / peaks["bf16_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": top["tflops"] / peaks["bf16_sustained"],
+                "traffic": NCU_TRAFFIC_BYTES.get(top["kernel"]) if Bl == 6144 else None,
+                "traffic_note": "bytes of one noun-path launch (M=36864) of this kernel, ncu --set full, profiles/",
                 "peak_source": peaks["source"] + " (sustained bf16; burst %.1f)" % peaks["bf16_burst"],
                 "launch_ms": top["ms_per_step"] / top["launches_per_step"],
                 "share_of_step": top["ms_per_step"] / ms_per_step,
-                "step_tflops_algorithmic": value * FLOP_PER_IMAGE_FWD_BWD / 1e12,
-                "step_frac": value * FLOP_PER_IMAGE_FWD_BWD / 1e12 / peaks["bf16_sustained"],
+                # per-GPU figures (the whole-job value divided by the number of GPUs)
+                "step_tflops_algorithmic": value * FLOP_PER_IMAGE_FWD_BWD / 1e12 / world,
+                "step_frac": value * FLOP_PER_IMAGE_FWD_BWD / 1e12 / world / peaks["bf16_sustained"],
                 # the neighbour projection W_p is folded into the gate weights (P_x = W_x W_p), so fewer FLOPs are
                 # executed than the algorithmic (aggregate-then-project) count the fraction above is quoted on
                 "step_tflops_executed": executed_flops_per_step / (ms_per_step * 1e-3) / 1e12 / world,

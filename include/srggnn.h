@@ -120,6 +120,13 @@ int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const f
 int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int B, const uint8_t* keep, float drop_p,
                       const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream);
 
+/* sr.py:80-83 on flat fp32 buffers of all trainable tensors (one launch instead of ~40 small ones):
+ * torch.nn.utils.clip_grad_norm_(params, max_norm) -- grads are scaled in place by min(1, max_norm / (||g||_2 + 1e-6)) --
+ * followed by torch.optim.Adamax(lr, betas = (beta1, beta2), eps).  scratch: device fp32 [2] = {||g||^2 of this step,
+ * number of steps taken so far (incremented by the call)}; n must be a multiple of 4. */
+int srg_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float max_norm, float* scratch, void* stream);
+
 /* Raw tensor-core GEMM (tests / micro-benchmarks):  C[M,N] = alpha * A[M,K] * B[N,K]^T + bias[N]
  * a_mn / b_mn = 1: the operand is stored transposed (A as [K,M], B as [K,N]).  c_dtype: SRG_DT_F32 | SRG_DT_BF16.
  * reduce = 1 (fp32 only): C += ... with k_splits-way split-K. */

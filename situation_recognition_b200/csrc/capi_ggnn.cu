@@ -2,6 +2,7 @@
 // orchestration.  Every contraction is one launch of the tcgen05 kernel in gemm.cuh; everything HBM-bound
 // is in kernels_elementwise.cu.
 #include <new>
+#include <vector>
 #include "elementwise.cuh"
 #include "host.cuh"
 #include "../../include/srggnn.h"
@@ -66,8 +67,8 @@ struct PathBufs {
   float* mask = nullptr;
   // backward
   float *dh = nullptr, *dh_acc = nullptr, *dx = nullptr;
-  bf16* dpre[2] = {};  // [M, 3D] column blocks [dpre_h | dpre_z | dpre_r], ping-pong over steps
-  bf16 *da = nullptr, *ada = nullptr, *dlb = nullptr;
+  bf16* dpre_all = nullptr;  // [T*M, 3D]: per step t (row offset t*M) the column blocks [dpre_h | dpre_z | dpre_r]
+  bf16 *da = nullptr, *ada = nullptr, *e = nullptr, *dlb = nullptr;
   float* G_P = nullptr;   // [3D, D] fp32: d/dP_x accumulated over the steps of this path
   bf16* G_Pb = nullptr;   // bf16 copy for the chain-rule GEMMs
   float* s_all = nullptr; // [3D]: c * colsum(dpre_x), for the W_x b_p bias term
@@ -89,6 +90,8 @@ struct Bump {
   }
 };
 
+inline bool base_is_null(const void* ws) { return ws == nullptr; }
+
 // Lay the buffers of one path out in `ws` (ws == nullptr: only compute the size).
 PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* ws) {
   PathBufs pb;
@@ -100,39 +103,44 @@ PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* w
   Bump bump(ws);
   pb.M = M;
   pb.h32 = bump.take<float>(MD);
+  // operand copies of the state, one per step boundary: ONE contiguous [(T+1)*M, D] array in training mode (the
+  // weight-gradient GEMMs read steps 0..T-1 as a single K = T*M operand), two ping-pong blocks otherwise
   const int n_hb = save ? T + 1 : 2;
-  bf16* hbh[kMaxT + 1];
-  bf16* hbm[kMaxT + 1];
-  bf16* hbl[kMaxT + 1];
-  for (int i = 0; i < n_hb; ++i) {
-    hbh[i] = bump.take<bf16>(MD);
-    hbm[i] = f32 ? bump.take<bf16>(MD) : nullptr;
-    hbl[i] = f32 ? bump.take<bf16>(MD) : nullptr;
-  }
+  bf16* hb_all = bump.take<bf16>(static_cast<size_t>(n_hb) * MD);
+  bf16* hb_mid_all = f32 ? bump.take<bf16>(static_cast<size_t>(n_hb) * MD) : nullptr;
+  bf16* hb_lo_all = f32 ? bump.take<bf16>(static_cast<size_t>(n_hb) * MD) : nullptr;
   for (int t = 0; t <= T; ++t) {
-    pb.hb_hi[t] = hbh[save ? t : (t & 1)];
-    pb.hb_mid[t] = hbm[save ? t : (t & 1)];
-    pb.hb_lo[t] = hbl[save ? t : (t & 1)];
+    const size_t off = static_cast<size_t>(save ? t : (t & 1)) * MD;
+    pb.hb_hi[t] = hb_all ? hb_all + off : nullptr;
+    pb.hb_mid[t] = hb_mid_all ? hb_mid_all + off : nullptr;
+    pb.hb_lo[t] = hb_lo_all ? hb_lo_all + off : nullptr;
   }
+  // per-step buffers; in training mode each kind is ONE contiguous [T*M, D] array (step t at row offset t*M), so the
+  // weight-gradient GEMMs can contract over all T steps in a single launch (K = T*M)
   const int n_st = save ? T : 1;
-  StepBufs sts[kMaxT];
-  for (int i = 0; i < n_st; ++i) {
-    StepBufs& s = sts[i];
-    if (mode == SRG_MODE_NOUN) {
-      s.a_hi = bump.take<bf16>(MD);
-      s.a_mid = f32 ? bump.take<bf16>(MD) : nullptr;
-      s.a_lo = f32 ? bump.take<bf16>(MD) : nullptr;
-    }
-    s.rh_hi = bump.take<bf16>(MD);
-    s.rh_mid = f32 ? bump.take<bf16>(MD) : nullptr;
-    s.rh_lo = f32 ? bump.take<bf16>(MD) : nullptr;
-    s.z = f32 ? static_cast<void*>(bump.take<float>(MD)) : static_cast<void*>(bump.take<bf16>(MD));
-    if (save) {
-      s.r = bump.take<bf16>(MD);
-      s.hc = bump.take<bf16>(MD);
-    }
+  const size_t n_all = static_cast<size_t>(n_st) * MD;
+  bf16* a_all = (mode == SRG_MODE_NOUN) ? bump.take<bf16>(n_all) : nullptr;
+  bf16* a_mid_all = (mode == SRG_MODE_NOUN && f32) ? bump.take<bf16>(n_all) : nullptr;
+  bf16* a_lo_all = (mode == SRG_MODE_NOUN && f32) ? bump.take<bf16>(n_all) : nullptr;
+  bf16* rh_all = bump.take<bf16>(n_all);
+  bf16* rh_mid_all = f32 ? bump.take<bf16>(n_all) : nullptr;
+  bf16* rh_lo_all = f32 ? bump.take<bf16>(n_all) : nullptr;
+  uint8_t* z_all = f32 ? reinterpret_cast<uint8_t*>(bump.take<float>(n_all)) : reinterpret_cast<uint8_t*>(bump.take<bf16>(n_all));
+  bf16* r_all = save ? bump.take<bf16>(n_all) : nullptr;
+  bf16* hc_all = save ? bump.take<bf16>(n_all) : nullptr;
+  for (int t = 0; t < T; ++t) {
+    const size_t off = (save ? static_cast<size_t>(t) : 0) * MD;
+    StepBufs& st = pb.st[t];
+    st.a_hi = a_all ? a_all + off : nullptr;
+    st.a_mid = a_mid_all ? a_mid_all + off : nullptr;
+    st.a_lo = a_lo_all ? a_lo_all + off : nullptr;
+    st.rh_hi = rh_all + off;
+    st.rh_mid = rh_mid_all ? rh_mid_all + off : nullptr;
+    st.rh_lo = rh_lo_all ? rh_lo_all + off : nullptr;
+    st.z = (base_is_null(ws)) ? nullptr : static_cast<void*>(z_all + off * (f32 ? 4 : 2));
+    st.r = r_all ? r_all + off : nullptr;
+    st.hc = hc_all ? hc_all + off : nullptr;
   }
-  for (int t = 0; t < T; ++t) pb.st[t] = sts[save ? t : 0];
   pb.xd_hi = bump.take<bf16>(MD);
   pb.xd_mid = f32 ? bump.take<bf16>(MD) : nullptr;
   pb.xd_lo = f32 ? bump.take<bf16>(MD) : nullptr;
@@ -142,10 +150,10 @@ PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* w
     pb.dh = bump.take<float>(MD);
     pb.dh_acc = bump.take<float>(MD);
     pb.dx = bump.take<float>(MD);
-    pb.dpre[0] = bump.take<bf16>(3 * MD);
-    pb.dpre[1] = bump.take<bf16>(3 * MD);
+    pb.dpre_all = bump.take<bf16>(static_cast<size_t>(T) * 3 * MD);
     pb.da = bump.take<bf16>(MD);
-    pb.ada = (mode == SRG_MODE_NOUN) ? bump.take<bf16>(MD) : nullptr;
+    pb.ada = bump.take<bf16>(MD);
+    pb.e = bump.take<bf16>(MD);
     pb.dlb = bump.take<bf16>(static_cast<size_t>(M) * npad);
     pb.G_P = bump.take<float>(static_cast<size_t>(3) * D * D);
     pb.G_Pb = bump.take<bf16>(static_cast<size_t>(3) * D * D);
@@ -365,16 +373,16 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
   // into the epilogue of the GEMM that completes dL/dh of step t (EPI_DH).
   // dpre[cur] = [dpre_h | dpre_z | dpre_r] as column blocks of one [M, 3D] matrix.
   float* dh_acc = pb.dh_acc;
-  int cur = 0;
+  auto dpre_of = [&](int t) { return pb.dpre_all + static_cast<size_t>(t) * M * ld3; };
   SRG_TRY(launch_gru_bwd_pre_ld(pb.dh, static_cast<const bf16*>(pb.st[T - 1].z), pb.st[T - 1].hc, pb.hb_hi[T - 1], M, D,
-                                pb.dpre[cur] + D, pb.dpre[cur], ld3, dh_acc, s));
+                                dpre_of(T - 1) + D, dpre_of(T - 1), ld3, dh_acc, s));
   for (int t = T - 1; t >= 0; --t) {
     StepBufs& st = pb.st[t];
-    bf16* dp = pb.dpre[cur];
+    bf16* dp = dpre_of(t);
     bf16* dpre_h = dp;
     bf16* dpre_z = dp + D;
     bf16* dpre_r = dp + 2 * D;
-    {  // d(r*h) = dpre_h U_h ; fused: dpre_r = drh*h*r*(1-r), dh_acc += drh*r
+    {  // d(r*h) = dpre_h U_h ; fused: dpre_r = drh*h*r*(1-r), e = drh*r (this path's share of dL/dh)
       GemmProblem p = base_problem(h, M, D);
       add_seg_ld(p, dp, M, ld3, ld3, 0, D);
       p.b_mn = true;
@@ -383,7 +391,7 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
       p.io[0] = mat(pb.hb_hi[t], M, D, D, DT_BF16);
       p.io[1] = mat(st.r, M, D, D, DT_BF16);
       p.io[2] = mat(dpre_r, M, D, ld3, DT_BF16);
-      p.io[3] = mat(dh_acc, M, D, D, DT_F32);
+      p.io[3] = mat(pb.e, M, D, D, DT_BF16);
       SRG_TRY(run_gemm(p, h->dev, s));
     }
     {  // da = [dpre_h | dpre_z | dpre_r] [P_h ; P_z ; P_r]   (gradient w.r.t. the aggregated state)
@@ -395,11 +403,11 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
       p.io[0] = mat(pb.da, M, D, D, DT_BF16);
       SRG_TRY(run_gemm(p, h->dev, s));
     }
-    const bf16* ada = pb.da;
-    if (mode == SRG_MODE_NOUN) {  // back through the aggregation: ada[b,j] = sum_i mask[b,i,j] da[b,i]
-      SRG_TRY(launch_aggregate_t_bf16(pb.da, pb.mask, B, R, D, pb.ada, s));
-      ada = pb.ada;
-    }
+    // back through the aggregation, plus the r*h share:  ada[b,j] = e[b,j] + sum_i mask[b,i,j] da[b,i]
+    // (verb node: the aggregation is the identity, mask == nullptr)
+    SRG_TRY(launch_aggregate_t_bf16(pb.da, (mode == SRG_MODE_NOUN) ? pb.mask : nullptr, pb.e,
+                                    (mode == SRG_MODE_NOUN) ? B : M, (mode == SRG_MODE_NOUN) ? R : 1, D, pb.ada, s));
+    const bf16* ada = pb.ada;
     {  // dL/dh_t = dh_acc + ada + [dpre_z | dpre_r] [U_z ; U_r], then the gate derivatives of step t-1
       GemmProblem p = base_problem(h, M, D);
       add_seg_ld(p, dp, M, ld3, ld3, D, 2 * D);
@@ -410,7 +418,7 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
       p.io[0] = mat(dh_acc, M, D, D, DT_F32);
       p.io[6] = mat(ada, M, D, D, DT_BF16);
       if (t > 0) {
-        bf16* dn = pb.dpre[cur ^ 1];
+        bf16* dn = dpre_of(t - 1);
         p.flags |= FLAG_NEXT;
         p.io[1] = mat(pb.st[t - 1].z, M, D, D, DT_BF16);
         p.io[2] = mat(pb.st[t - 1].hc, M, D, D, DT_BF16);
@@ -420,17 +428,20 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
       }
       SRG_TRY(run_gemm(p, h->dev, s));
     }
-    // ---- weight gradients of this step
-    const bf16* a_in = (mode == SRG_MODE_NOUN) ? st.a_hi : pb.hb_hi[t];
-    SRG_TRY(wgrad(h, dp, ld3, 3 * D, a_in, D, M, pb.G_P, s));              // dP_h, dP_z, dP_r in one GEMM
-    SRG_TRY(wgrad(h, dpre_z, ld3, D, pb.hb_hi[t], D, M, g->U_z, s));
-    SRG_TRY(wgrad(h, dpre_r, ld3, D, pb.hb_hi[t], D, M, g->U_r, s));
-    SRG_TRY(wgrad(h, dpre_h, ld3, D, st.rh_hi, D, M, g->U_h, s));
-    ColsumJob jobs[3] = {{dpre_h, g->b_Wh, g->b_Uh, 1.f, pb.s_all, cmul},
-                         {dpre_z, g->b_Wz, g->b_Uz, 1.f, pb.s_all + D, cmul},
-                         {dpre_r, g->b_Wr, g->b_Ur, 1.f, pb.s_all + 2 * D, cmul}};
-    SRG_TRY(launch_colsum_multi(jobs, 3, ld3, M, D, s));
-    cur ^= 1;
+  }
+  // ---- weight gradients: one GEMM per weight group, contracting over all T steps at once (K = T*M rows)
+  {
+    const int KM = T * M;
+    bf16* dp = pb.dpre_all;
+    const bf16* a_all = (mode == SRG_MODE_NOUN) ? pb.st[0].a_hi : pb.hb_hi[0];   // contiguous over t = 0..T-1
+    SRG_TRY(wgrad(h, dp, ld3, 3 * D, a_all, D, KM, pb.G_P, s));              // dP_h, dP_z, dP_r in one GEMM
+    SRG_TRY(wgrad(h, dp + D, ld3, D, pb.hb_hi[0], D, KM, g->U_z, s));
+    SRG_TRY(wgrad(h, dp + 2 * D, ld3, D, pb.hb_hi[0], D, KM, g->U_r, s));
+    SRG_TRY(wgrad(h, dp, ld3, D, pb.st[0].rh_hi, D, KM, g->U_h, s));
+    ColsumJob jobs[3] = {{dp, g->b_Wh, g->b_Uh, 1.f, pb.s_all, cmul},
+                         {dp + D, g->b_Wz, g->b_Uz, 1.f, pb.s_all + D, cmul},
+                         {dp + 2 * D, g->b_Wr, g->b_Ur, 1.f, pb.s_all + 2 * D, cmul}};
+    SRG_TRY(launch_colsum_multi(jobs, 3, ld3, KM, D, s));
   }
   pb.dh = dh_acc;  // gradient w.r.t. the initial node states
 
@@ -600,30 +611,42 @@ int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* st
   h->params = *p;
   const size_t DD = static_cast<size_t>(D) * D;
 
-  // (1) bf16 parts (hi, mid, lo) of the message-side weights, stacked [W_h; W_z; W_r], and of W_p in block order kPartB
+  // All fp32 -> bf16 conversions of this call are queued as jobs and run as two launches (before / after the P GEMM).
+  std::vector<PackJob> jobs;
+  auto queue = [&](const float* src, int rows, int rows_pad, bf16* dst, int64_t ld, int64_t col_off, int part) {
+    PackJob j;
+    j.src = src; j.dst = dst; j.ld_dst = ld; j.col_off = col_off; j.rows = rows; j.rows_pad = rows_pad; j.part = part;
+    jobs.push_back(j);
+  };
+  const bool f32 = (precision == SRG_PREC_FP32);
+
+  // (1) bf16 parts (hi, mid, lo) of the message-side weights, stacked [W_h; W_z; W_r], and of W_p in block order kPartB.
+  //     The training mode only needs the hi parts.
   const float* Wm32[3] = {p->W_h, p->W_z, p->W_r};
   bf16* Wm_part[3] = {h->Wm_hi, h->Wm_mid, h->Wm_lo};
+  const int p_terms = f32 ? kSplitTerms : 1;
   for (int x = 0; x < 3; ++x)
-    for (int part = 0; part < 3; ++part)
-      SRG_TRY(launch_pack_weight(Wm32[x], D, D, D, Wm_part[part] + x * DD, D, 0, part, s));
-  for (int b = 0; b < kSplitTerms; ++b)
-    SRG_TRY(launch_pack_weight(p->W_p, D, D, D, h->Wp6 + b * DD, D, 0, kPartB[b], s));
+    for (int part = 0; part < (f32 ? 3 : 1); ++part) queue(Wm32[x], D, D, Wm_part[part] + x * DD, D, 0, part);
+  for (int b = 0; b < p_terms; ++b) queue(p->W_p, D, D, h->Wp6 + b * DD, D, 0, kPartB[b]);
+  SRG_TRY(launch_pack_weight_multi(jobs.data(), static_cast<int>(jobs.size()), D, s));
+  jobs.clear();
 
-  // (2) P = [W_h; W_z; W_r] W_p, fp32-accurate through the split (3 leading terms are enough for the bf16 operands of
-  //     the training mode, all 6 for the fp32-parity mode), written as bf16 hi + mid + lo
+  // (2) P = [W_h; W_z; W_r] W_p.  Training mode: one bf16 x bf16 product with fp32 accumulation (the same operand
+  //     rounding the unfused formulation has); fp32-parity mode: all six split terms, written as bf16 hi + mid + lo.
   {
-    const int terms = (precision == SRG_PREC_FP32) ? kSplitTerms : 3;
     GemmProblem g = base_problem(h, 3 * D, D);
-    for (int b = 0; b < terms; ++b) add_seg(g, Wm_part[kPartA[b]], 3 * D, D, 0, D);
-    g.corr_seg_begin = 1;
+    for (int b = 0; b < p_terms; ++b) add_seg(g, Wm_part[kPartA[b]], 3 * D, D, 0, D);
+    if (f32) g.corr_seg_begin = 1;
     g.b_mn = true;                                   // B[n = i, k] = W_p[k, i]: W_p as stored, K along rows
-    g.b = mat(h->Wp6, static_cast<int64_t>(terms) * D, D, D, DT_BF16);
+    g.b = mat(h->Wp6, static_cast<int64_t>(p_terms) * D, D, D, DT_BF16);
     g.epi = EPI_STORE_BF16;
-    g.f32 = true;                                    // instantiation with the 3-way split output
-    g.flags = FLAG_LO;
+    g.f32 = f32;                                     // instantiation with the 3-way split output
+    g.flags = f32 ? FLAG_LO : 0;
     g.io[0] = mat(h->P_hi, 3 * D, D, D, DT_BF16);
-    g.io[1] = mat(h->P_mid, 3 * D, D, D, DT_BF16);
-    g.io[2] = mat(h->P_lo, 3 * D, D, D, DT_BF16);
+    if (f32) {
+      g.io[1] = mat(h->P_mid, 3 * D, D, D, DT_BF16);
+      g.io[2] = mat(h->P_lo, 3 * D, D, D, DT_BF16);
+    }
     SRG_TRY(run_gemm(g, h->dev, s));
   }
 
@@ -631,12 +654,10 @@ int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* st
   const int64_t ld1 = static_cast<int64_t>(D) * split, ld2 = static_cast<int64_t>(2 * D) * split;
   const bf16* P_part[3] = {h->P_hi, h->P_mid, h->P_lo};
   auto pack_u = [&](const float* src, int rows, int rows_pad, bf16* dst, int64_t ld, int64_t row_off, int block_cols,
-                    int col_in_block) -> int {
+                    int col_in_block) {
     bf16* d = dst + row_off * ld;
     for (int b = 0; b < split; ++b)
-      SRG_TRY(launch_pack_weight(src, rows, D, rows_pad, d, ld, static_cast<int64_t>(b) * block_cols + col_in_block,
-                                 kPartB[b], s));
-    return SRG_OK;
+      queue(src, rows, rows_pad, d, ld, static_cast<int64_t>(b) * block_cols + col_in_block, kPartB[b]);
   };
   auto pack_p = [&](int x, bf16* dst, int64_t row_off) -> int {  // x: 0 = h, 1 = z, 2 = r
     for (int b = 0; b < split; ++b)
@@ -644,18 +665,19 @@ int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* st
     return SRG_OK;
   };
   SRG_TRY(pack_p(1, h->Wzr, 0));
-  SRG_TRY(pack_u(p->U_z, D, D, h->Wzr, ld2, 0, 2 * D, D));
+  pack_u(p->U_z, D, D, h->Wzr, ld2, 0, 2 * D, D);
   SRG_TRY(pack_p(2, h->Wzr, D));
-  SRG_TRY(pack_u(p->U_r, D, D, h->Wzr, ld2, D, 2 * D, D));
+  pack_u(p->U_r, D, D, h->Wzr, ld2, D, 2 * D, D);
   SRG_TRY(pack_p(0, h->Wh, 0));
-  SRG_TRY(pack_u(p->U_h, D, D, h->Wh, ld2, 0, 2 * D, D));
-  SRG_TRY(pack_u(p->Wc_noun, h->L, h->Lpad, h->Wcn, ld1, 0, D, 0));
-  SRG_TRY(pack_u(p->Wc_verb, h->V, h->Vpad, h->Wcv, ld1, 0, D, 0));
-  if (precision == SRG_PREC_BF16) {  // backward operands (MN-major B = stacks along K)
-    SRG_TRY(launch_pack_weight(p->U_z, D, D, D, h->U_stack, D, 0, 0, s));
-    SRG_TRY(launch_pack_weight(p->U_r, D, D, D, h->U_stack + DD, D, 0, 0, s));
-    SRG_TRY(launch_pack_weight(p->U_h, D, D, D, h->Uh, D, 0, 0, s));
+  pack_u(p->U_h, D, D, h->Wh, ld2, 0, 2 * D, D);
+  pack_u(p->Wc_noun, h->L, h->Lpad, h->Wcn, ld1, 0, D, 0);
+  pack_u(p->Wc_verb, h->V, h->Vpad, h->Wcv, ld1, 0, D, 0);
+  if (!f32) {  // backward operands (MN-major B = stacks along K)
+    queue(p->U_z, D, D, h->U_stack, D, 0, 0);
+    queue(p->U_r, D, D, h->U_stack + DD, D, 0, 0);
+    queue(p->U_h, D, D, h->Uh, D, 0, 0);
   }
+  SRG_TRY(launch_pack_weight_multi(jobs.data(), static_cast<int>(jobs.size()), D, s));
 
   // (4) biases: b'_x(mode) = b_Wx + b_Ux + c W_x b_p, c = R for the noun graph (model.py:73-75: the projection bias is
   //     added for all R neighbours before the sum), c = 1 for the verb node (model.py:62-64)
@@ -738,6 +760,13 @@ int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t
   SRG_CHECK(ldl >= h->V, "srg_verb_loss: ldl %lld < n_verbs %d", (long long)ldl, h->V);
   return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, loss, dlogits, grad_scale,
                         static_cast<cudaStream_t>(stream));
+}
+
+int srg_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float max_norm, float* scratch, void* stream) {
+  SRG_CHECK(params && grads && exp_avg && exp_inf && scratch, "srg_clip_adamax: null argument");
+  return launch_clip_adamax(params, grads, exp_avg, exp_inf, n, lr, beta1, beta2, eps, max_norm, scratch, scratch + 1,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const float* feat, const int64_t* verb, int B,

@@ -33,6 +33,16 @@ int launch_aggregate_bwd(const float* dh_acc, const float* da, const float* mask
 // dst[r, col_off + c] = bf16 part `want_lo` (0 hi, 1 mid, 2 lo) of src[r, c] (r < rows), 0 for rows <= r < rows_pad
 int launch_pack_weight(const float* src, int rows, int cols, int rows_pad, bf16* dst, int64_t ld_dst, int64_t col_off,
                        int want_lo, cudaStream_t s);
+// many pack_weight jobs in one launch (all with `cols` columns)
+struct PackJob {
+  const float* src;
+  bf16* dst;
+  int64_t ld_dst;
+  int64_t col_off;
+  int rows, rows_pad, part;
+};
+constexpr int kMaxPackJobs = 48;
+int launch_pack_weight_multi(const PackJob* jobs, int n_jobs, int cols, cudaStream_t s);
 // dst[i] = a[i] (+ b[i]) for i < n, 0 for n <= i < n_pad
 int launch_pack_bias(const float* a, const float* b, int n, int n_pad, float* dst, cudaStream_t s);
 
@@ -62,8 +72,9 @@ int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, c
                          const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_roles, int B,
                          int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s);
 
-// adm[b,j,:] = sum_i mask[b,i,j] * dm[b,i,:]   (bf16 in / bf16 out; the aggregation commutes with the W_p GEMM)
-int launch_aggregate_t_bf16(const bf16* dm, const float* mask, int B, int R, int D, bf16* adm, cudaStream_t s);
+// adm[b,j,:] = add[b,j,:] + sum_i mask[b,i,j] * dm[b,i,:]   (bf16 in / bf16 out; mask == nullptr: identity, R = 1)
+int launch_aggregate_t_bf16(const bf16* dm, const float* mask, const bf16* add, int B, int R, int D, bf16* adm,
+                            cudaStream_t s);
 // up to 4 column sums in one launch: out1/out2 += scale * colsum, out3 += scale3 * colsum
 struct ColsumJob {
   const bf16* X;
@@ -76,6 +87,10 @@ struct ColsumJob {
 int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows, int n_cols, cudaStream_t s);
 
 int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s);
+
+// clip_grad_norm_(max_norm) + Adamax on flat fp32 buffers (sr.py:80-83).  scratch: device fp32 [2] = {sum g^2, step}.
+int launch_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float max_norm, float* norm_sq, float* step, cudaStream_t s);
 
 // GRU backward prologue writing into column blocks of a wider matrix (leading dimension ld_out elements)
 int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int rows, int D,

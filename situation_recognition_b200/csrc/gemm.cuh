@@ -35,7 +35,7 @@ enum EpiKind : int {
   EPI_ZR = 2,          // GRU update/reset gates:  z = sig(.), r = sig(.), rh = r*h
   EPI_H = 3,           // GRU candidate + state update: hc = tanh(.), h' = h + z*(hc - h)
   EPI_LOGITS = 4,      // classifier: logits + per-tile row softmax statistics
-  EPI_DRH = 5,         // backward: drh = acc; dpre_r = drh*h*r*(1-r); dh_acc += drh*r
+  EPI_DRH = 5,         // backward: drh = acc; dpre_r = drh*h*r*(1-r); e = drh*r
   EPI_DH = 6,          // backward: g = acc + dh_acc = dL/dh_{t-1}'; fused GRU-gate derivatives of step t-1
 };
 
@@ -73,7 +73,7 @@ struct EpiTraits {
                                 : (EPI == EPI_H)         ? (F32 ? 7 : 4)
                                 : (EPI == EPI_LOGITS)    ? 4
                                 : (EPI == EPI_DH)        ? 6
-                                                         : 6;
+                                                         : 4;
 };
 
 template <int CG, int BLOCK_N, int EPI, bool F32>
@@ -210,8 +210,8 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
   uint64_t* empty_bar = bars + STAGES;            // [STAGES]
   uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [2]
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]     (used in the leader CTA)
-  uint64_t* epi_in_bar = bars + 2 * STAGES + 4;   // [4] one per epilogue warp
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+  uint64_t* epi_in_bar = bars + 2 * STAGES + 4;   // [8] two per epilogue warp (ping-pong input sets)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -242,7 +242,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
       ptx::mbar_init(&tmem_empty_bar[i], CG * 128);
     }
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(&epi_in_bar[i], 1);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&epi_in_bar[i], 1);
     ptx::fence_barrier_init();
   }
   if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
@@ -372,8 +372,11 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
     const uint32_t slot0 = ptx::smem_u32(smem_epi + ew * SLOTS * kSlotBytes);
     auto slot = [&](int i) -> uint32_t { return slot0 + i * kSlotBytes; };
     auto slot_ptr = [&](int i) -> void* { return smem_epi + (ew * SLOTS + i) * kSlotBytes; };
-    uint64_t* in_bar = &epi_in_bar[ew];
+    uint64_t* in_bar = &epi_in_bar[ew * 2];
     uint32_t in_phase = 0;
+    uint32_t in_phase2 = 0;    // EPI_DRH: phase bits of the two ping-pong input sets
+    bool pre_issued = false;   // EPI_DRH: the loads of the coming tile's first chunk are already in flight
+    (void)in_phase2; (void)pre_issued;
     int iter = 0;
     int store_set = 0;  // ping-pong for pure store epilogues
     (void)in_bar; (void)in_phase; (void)store_set;
@@ -648,46 +651,74 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
           }
         } else if constexpr (EPI == EPI_DRH) {
           // backward of rh = r*h:  drh = acc.
-          //   io0 = h (bf16 in), io1 = r (bf16 in), io2 = dpre_r (bf16 out) = drh*h*r*(1-r),
-          //   io3 = dh_acc fp32 (read-modify-write in place): += drh*r
-          constexpr int S_H = 0, S_R = 1, S_DP = 2, S_DH = 3;
+          //   io0 = h (bf16 in), io1 = r (bf16 in); io2 = dpre_r (bf16 out) = drh*h*r*(1-r), io3 = e (bf16 out) = drh*r
+          //   (e is the contribution of this path to dL/dh; it is added when dL/dh is completed, EPI_DH).
+          // Both outputs overwrite their inputs in shared memory, so a chunk needs two slots; two sets ping-pong and
+          // the loads of the NEXT chunk (of this tile or of the warp's next tile) are issued before this one is
+          // processed, which takes the TMA load latency off the critical path of this short-K GEMM.
+          constexpr int NCH = BLOCK_N / 64;
+          static_assert(NCH % 2 == 0, "ping-pong sets assume an even number of column chunks per tile");
+          const int set = cc & 1;
+          auto issue = [&](int st, int col, int row) {
+            ptx::mbar_arrive_expect_tx(&in_bar[st], 2 * kSlotBytes);
+            ptx::tma_load_2d(&maps.io[0], &in_bar[st], slot_ptr(2 * st), col, row);
+            ptx::tma_load_2d(&maps.io[1], &in_bar[st], slot_ptr(2 * st + 1), col, row);
+          };
           if (lane == 0) {
-            ptx::tma_wait_group_read<0>();
-            ptx::mbar_arrive_expect_tx(in_bar, 4 * kSlotBytes);
-            ptx::tma_load_2d(&maps.io[0], in_bar, slot_ptr(S_H), gcol, row0);
-            ptx::tma_load_2d(&maps.io[1], in_bar, slot_ptr(S_R), gcol, row0);
-            ptx::tma_load_2d(&maps.io[3], in_bar, slot_ptr(S_DH), gcol, row0);
-            ptx::tma_load_2d(&maps.io[3], in_bar, slot_ptr(S_DH + 1), gcol + 32, row0);
+            if (cc == 0 && !pre_issued) {
+              ptx::tma_wait_group_read<0>();
+              issue(0, gcol, row0);
+            }
+            // next chunk in sequence -> the other set (its previous stores were committed one iteration ago)
+            if (cc + 1 < NCH) {
+              ptx::tma_wait_group_read<0>();
+              issue(set ^ 1, gcol + 64, row0);
+            } else {
+              const int w2 = w + num_clusters;
+              if (w2 < total_work) {
+                const int nt2 = (w2 % tiles_mn) % num_n_tiles, mt2 = (w2 % tiles_mn) / num_n_tiles;
+                const int row2 = mt2 * kTileM * CG + static_cast<int>(cta_rank) * kTileM + ew * 32;
+                if (row2 < args.M) {
+                  ptx::tma_wait_group_read<0>();
+                  issue(set ^ 1, nt2 * BLOCK_N, row2);
+                }
+              }
+            }
           }
-          ptx::mbar_wait(in_bar, in_phase);
-          in_phase ^= 1u;
+          if (cc + 1 == NCH) {  // warp-uniform copy of the decision taken by lane 0 above
+            const int w2 = w + num_clusters;
+            pre_issued = false;
+            if (w2 < total_work) {
+              const int mt2 = (w2 % tiles_mn) / num_n_tiles;
+              pre_issued = (mt2 * kTileM * CG + static_cast<int>(cta_rank) * kTileM + ew * 32) < args.M;
+            }
+          }
+          ptx::mbar_wait(&in_bar[set], (in_phase2 >> set) & 1u);
+          in_phase2 ^= (1u << set);
+          const uint32_t s_h = slot(2 * set), s_r = slot(2 * set + 1);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             load_acc(cc * 64 + half * 32, accv);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              float h[8], r[8], dh[8], dp[8];
-              slot_ld_bf16x8(slot(S_H), lane, half * 4 + g, h);
-              slot_ld_bf16x8(slot(S_R), lane, half * 4 + g, r);
-              slot_ld_f32x8(slot(S_DH + half), lane, g, dh);
+              float h[8], r[8], e[8], dp[8];
+              slot_ld_bf16x8(s_h, lane, half * 4 + g, h);
+              slot_ld_bf16x8(s_r, lane, half * 4 + g, r);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float d = accv[g * 8 + i];
                 dp[i] = d * h[i] * r[i] * (1.0f - r[i]);
-                dh[i] = fmaf(d, r[i], dh[i]);
+                e[i] = d * r[i];
               }
-              slot_st_bf16x8(slot(S_DP), lane, half * 4 + g, dp);
-              slot_st_f32x8(slot(S_DH + half), lane, g, dh);
+              slot_st_bf16x8(s_h, lane, half * 4 + g, dp);
+              slot_st_bf16x8(s_r, lane, half * 4 + g, e);
             }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (warp_active) {
-              ptx::tma_store_2d(&maps.io[2], slot_ptr(S_DP), gcol, row0);
-              ptx::tma_store_2d(&maps.io[3], slot_ptr(S_DH), gcol, row0);
-              ptx::tma_store_2d(&maps.io[3], slot_ptr(S_DH + 1), gcol + 32, row0);
-            }
+            ptx::tma_store_2d(&maps.io[2], slot_ptr(2 * set), gcol, row0);
+            ptx::tma_store_2d(&maps.io[3], slot_ptr(2 * set + 1), gcol, row0);
             ptx::tma_commit_group();
           }
         } else if constexpr (EPI == EPI_DH) {

@@ -201,6 +201,28 @@ __global__ void k_pack_weight(const float* __restrict__ src, int rows, int cols,
   }
 }
 
+struct PackJobs {
+  PackJob j[kMaxPackJobs];
+};
+// grid = (blocks per job, jobs)
+__global__ void k_pack_weight_multi(PackJobs jobs, int cols) {
+  const PackJob job = jobs.j[blockIdx.y];
+  const int c4 = cols / 4;
+  const int64_t total = static_cast<int64_t>(job.rows_pad) * c4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(t / c4);
+    const int c = static_cast<int>(t % c4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < job.rows) v = *reinterpret_cast<const float4*>(job.src + static_cast<int64_t>(r) * cols + c);
+    for (int k = 0; k < job.part; ++k) {
+      v.x -= bf16_round(v.x); v.y -= bf16_round(v.y); v.z -= bf16_round(v.z); v.w -= bf16_round(v.w);
+    }
+    *reinterpret_cast<uint2*>(job.dst + static_cast<int64_t>(r) * job.ld_dst + job.col_off + c) =
+        pack4_bf16(v.x, v.y, v.z, v.w);
+  }
+}
+
 __global__ void k_pack_bias(const float* __restrict__ a, const float* __restrict__ b, int n, int n_pad,
                             float* __restrict__ dst) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
@@ -460,8 +482,8 @@ __global__ void k_node_init_bwd(const float* __restrict__ dh0, const bf16* __res
   }
 }
 
-__global__ void k_aggregate_t_bf16(const bf16* __restrict__ dm, const float* __restrict__ mask, int B, int R, int D,
-                                   bf16* __restrict__ adm) {
+__global__ void k_aggregate_t_bf16(const bf16* __restrict__ dm, const float* __restrict__ mask,
+                                   const bf16* __restrict__ add, int B, int R, int D, bf16* __restrict__ adm) {
   const int D8 = D / 8;
   const int64_t total = static_cast<int64_t>(B) * D8;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
@@ -477,15 +499,20 @@ __global__ void k_aggregate_t_bf16(const bf16* __restrict__ dm, const float* __r
         g[i][4] = bf16_lo_f(u.z); g[i][5] = bf16_hi_f(u.z); g[i][6] = bf16_lo_f(u.w); g[i][7] = bf16_hi_f(u.w);
       }
     }
-    const float* mb = mask + static_cast<int64_t>(b) * R * R;
+    const float* mb = (mask != nullptr) ? mask + static_cast<int64_t>(b) * R * R : nullptr;
 #pragma unroll
     for (int j = 0; j < kMaxR; ++j) {
       if (j < R) {
-        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float a[8];
+        {
+          const uint4 u = *reinterpret_cast<const uint4*>(add + (static_cast<int64_t>(b) * R + j) * D + d);
+          a[0] = bf16_lo_f(u.x); a[1] = bf16_hi_f(u.x); a[2] = bf16_lo_f(u.y); a[3] = bf16_hi_f(u.y);
+          a[4] = bf16_lo_f(u.z); a[5] = bf16_hi_f(u.z); a[6] = bf16_lo_f(u.w); a[7] = bf16_hi_f(u.w);
+        }
 #pragma unroll
         for (int i = 0; i < kMaxR; ++i) {
           if (i < R) {
-            const float m = __ldg(mb + i * R + j);
+            const float m = (mb != nullptr) ? __ldg(mb + i * R + j) : 1.0f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) a[k] = fmaf(m, g[i][k], a[k]);
           }
@@ -627,6 +654,60 @@ __global__ void k_pack_bias3(const float* __restrict__ a, const float* __restric
   }
 }
 
+__global__ void k_sumsq(const float* __restrict__ g, int64_t n4, float* __restrict__ out) {
+  __shared__ float red[kThreads / 32];
+  float acc = 0.f;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(g + t * 4);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+
+// torch.nn.utils.clip_grad_norm_ (coef = min(1, max_norm / (norm + 1e-6)), grads scaled in place) followed by
+// torch.optim.Adamax: exp_avg = b1*exp_avg + (1-b1)*g; exp_inf = max(b2*exp_inf, |g| + eps);
+// p -= lr / (1 - b1^step) * exp_avg / exp_inf.   `step` holds the number of steps taken BEFORE this one.
+__global__ void k_clip_adamax(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                              float* __restrict__ u, int64_t n4, float lr, float b1, float b2, float eps,
+                              float max_norm, const float* __restrict__ norm_sq, const float* __restrict__ step) {
+  const float norm = sqrtf(*norm_sq);
+  const float coef = fminf(1.0f, max_norm / (norm + 1e-6f));
+  const float t = *step + 1.0f;
+  const float clr = lr / (1.0f - powf(b1, t));
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 gv = *reinterpret_cast<const float4*>(g + i * 4);
+    float4 mv = *reinterpret_cast<const float4*>(m + i * 4);
+    float4 uv = *reinterpret_cast<const float4*>(u + i * 4);
+    float4 pv = *reinterpret_cast<const float4*>(p + i * 4);
+    float* gp = reinterpret_cast<float*>(&gv);
+    float* mp = reinterpret_cast<float*>(&mv);
+    float* up = reinterpret_cast<float*>(&uv);
+    float* pp = reinterpret_cast<float*>(&pv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      gp[k] *= coef;
+      mp[k] = b1 * mp[k] + (1.0f - b1) * gp[k];
+      up[k] = fmaxf(b2 * up[k], fabsf(gp[k]) + eps);
+      pp[k] -= clr * (mp[k] / up[k]);
+    }
+    *reinterpret_cast<float4*>(g + i * 4) = gv;
+    *reinterpret_cast<float4*>(m + i * 4) = mv;
+    *reinterpret_cast<float4*>(u + i * 4) = uv;
+    *reinterpret_cast<float4*>(p + i * 4) = pv;
+  }
+}
+
+__global__ void k_inc(float* x) { *x += 1.0f; }
+
 __global__ void k_fill_f32(float* p, int64_t n, float v) {
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -703,6 +784,18 @@ int launch_pack_weight(const float* src, int rows, int cols, int rows_pad, bf16*
   k_pack_weight<<<grid_for(static_cast<int64_t>(rows_pad) * cols / 2), kThreads, 0, s>>>(src, rows, cols, rows_pad,
                                                                                         dst, ld_dst, col_off, want_lo);
   SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_pack_weight_multi(const PackJob* jobs, int n_jobs, int cols, cudaStream_t s) {
+  for (int j0 = 0; j0 < n_jobs; j0 += kMaxPackJobs) {
+    const int n = (n_jobs - j0 < kMaxPackJobs) ? n_jobs - j0 : kMaxPackJobs;
+    PackJobs js;
+    for (int i = 0; i < kMaxPackJobs; ++i) js.j[i] = jobs[j0 + (i < n ? i : 0)];
+    dim3 grid(296, n);
+    k_pack_weight_multi<<<grid, kThreads, 0, s>>>(js, cols);
+    SRG_LAUNCH_CHECK();
+  }
   return SRG_OK;
 }
 
@@ -795,10 +888,11 @@ int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, c
   return SRG_OK;
 }
 
-int launch_aggregate_t_bf16(const bf16* dm, const float* mask, int B, int R, int D, bf16* adm, cudaStream_t s) {
+int launch_aggregate_t_bf16(const bf16* dm, const float* mask, const bf16* add, int B, int R, int D, bf16* adm,
+                            cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
-  k_aggregate_t_bf16<<<grid_for(static_cast<int64_t>(B) * D / 8), kThreads, 0, s>>>(dm, mask, B, R, D, adm);
+  k_aggregate_t_bf16<<<grid_for(static_cast<int64_t>(B) * D / 8), kThreads, 0, s>>>(dm, mask, add, B, R, D, adm);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
@@ -847,6 +941,21 @@ int launch_outer_acc(const float* sv, const float* b, int rows, int cols, float*
 int launch_pack_bias3(const float* a, const float* b, const float* c, float scale, int n, int n_pad, float* dst,
                       cudaStream_t s) {
   k_pack_bias3<<<grid_for(n_pad), kThreads, 0, s>>>(a, b, c, scale, n, n_pad, dst);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float max_norm, float* norm_sq, float* step, cudaStream_t s) {
+  if (n <= 0) return SRG_OK;
+  if (n % 4 != 0) return set_error(SRG_ERR_ARG, "clip_adamax: flat length %lld must be a multiple of 4", (long long)n);
+  SRG_CUDA(cudaMemsetAsync(norm_sq, 0, sizeof(float), s));
+  k_sumsq<<<grid_for(n / 4, kThreads, 148 * 4), kThreads, 0, s>>>(grads, n / 4, norm_sq);
+  SRG_LAUNCH_CHECK();
+  k_clip_adamax<<<grid_for(n / 4), kThreads, 0, s>>>(params, grads, exp_avg, exp_inf, n / 4, lr, beta1, beta2, eps,
+                                                     max_norm, norm_sq, step);
+  SRG_LAUNCH_CHECK();
+  k_inc<<<1, 1, 0, s>>>(step);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }

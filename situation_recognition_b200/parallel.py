@@ -53,3 +53,85 @@ def attach(model, group=None):
     else:
         model.loss_group = None
     return FlatGrads(model.parameters())
+
+
+class FlatParams(FlatGrads):
+    """Parameters AND gradients of the trainable tensors as two flat fp32 buffers (each tensor keeps its shape as a
+    view), so clip + optimizer run as one fused kernel over contiguous memory (`FlatAdamax`)."""
+
+    def __init__(self, params):
+        params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in params)
+        n_pad = (n + 3) // 4 * 4
+        ref = params[0]
+        self.flat_param = torch.zeros(n_pad, dtype=ref.dtype, device=ref.device)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                view = self.flat_param[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                off += p.numel()
+        self.params = params
+        self.flat = torch.zeros(n_pad, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+
+class FlatAdamax(torch.optim.Optimizer):
+    """`clip_grad_norm_(params, max_norm)` + `torch.optim.Adamax` (sr.py:80-83,472-473) as ONE fused CUDA kernel over the
+    flat buffers of `FlatParams` (srg_clip_adamax).  The per-parameter state (`step`, `exp_avg`, `exp_inf`) is exposed
+    through the usual `state_dict()` so checkpoints stay interchangeable with torch.optim.Adamax."""
+
+    def __init__(self, flat, lr=0.002, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
+        if not isinstance(flat, FlatParams):
+            raise TypeError("FlatAdamax needs parallel.FlatParams")
+        super().__init__(flat.params, dict(lr=lr, betas=betas, eps=eps, max_norm=max_norm))
+        self.flat = flat
+        dev = flat.flat.device
+        self.exp_avg = torch.zeros_like(flat.flat)
+        self.exp_inf = torch.zeros_like(flat.flat)
+        self.scratch = torch.zeros(2, dtype=torch.float32, device=dev)   # {||g||^2, steps taken}
+        off = 0
+        for p in flat.params:
+            n = p.numel()
+            self.state[p] = {"step": self.scratch[1], "exp_avg": self.exp_avg[off:off + n].view_as(p),
+                             "exp_inf": self.exp_inf[off:off + n].view_as(p)}
+            off += n
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import _lib
+        g = self.param_groups[0]
+        lib = _lib.load()
+        _lib.check(lib.srg_clip_adamax(_lib.ptr(self.flat.flat_param), _lib.ptr(self.flat.flat), _lib.ptr(self.exp_avg),
+                                       _lib.ptr(self.exp_inf), self.flat.flat.numel(), g["lr"], g["betas"][0],
+                                       g["betas"][1], g["eps"], g["max_norm"], _lib.ptr(self.scratch),
+                                       _lib.stream_ptr()))
+
+    def total_norm(self):
+        """Gradient norm seen by the last step (before clipping), like the return value of clip_grad_norm_."""
+        return self.scratch[0].sqrt()
+
+    def state_dict(self):
+        sd = super().state_dict()
+        for st in sd["state"].values():       # materialise views so the checkpoint does not alias the live buffers
+            for k in list(st):
+                st[k] = st[k].detach().clone()
+        return sd
+
+    def load_state_dict(self, state_dict):
+        groups = state_dict["param_groups"]
+        ids = [i for grp in groups for i in grp["params"]]
+        for pid, p in zip(ids, self.flat.params):
+            st = state_dict["state"].get(pid)
+            if st is None:
+                continue
+            self.state[p]["exp_avg"].copy_(st["exp_avg"])
+            self.state[p]["exp_inf"].copy_(st["exp_inf"])
+            self.scratch[1] = float(st["step"])
+        for k in ("lr", "betas", "eps"):
+            if k in groups[0]:
+                self.param_groups[0][k] = groups[0][k]

@@ -291,3 +291,33 @@ def test_graphed_step_matches_eager(enc_syn):
         results.append((torch.stack(losses).cpu(), {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
     (l0, p0), (l1, p1) = results
     assert torch.allclose(l0[0], l1[0], rtol=1e-5, atol=1e-6)          # first step: identical weights and masks
+
+
+def test_fused_clip_adamax_matches_torch(enc_syn):
+    """srg_clip_adamax (one kernel over the flat buffers) against clip_grad_norm_ + torch.optim.Adamax, 3 steps."""
+    from situation_recognition_b200 import parallel
+    torch.manual_seed(0)
+    a = S.FCGGNN(enc_syn, 256, backbone=None).cuda()
+    b = S.FCGGNN(enc_syn, 256, backbone=None).cuda()
+    b.load_state_dict(a.state_dict())
+    fa = parallel.FlatParams(a.parameters())
+    opt_a = parallel.FlatAdamax(fa, lr=0.002, max_norm=1.0)
+    opt_b = torch.optim.Adamax(b.parameters(), lr=0.002)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for step in range(3):
+        scale = 10.0 if step == 0 else 1e-3          # first step clips, later ones do not
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            grad = torch.randn(pa.shape, device="cuda", generator=g) * scale
+            pa.grad.copy_(grad)
+            pb.grad = grad.clone()
+        norm_b = torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
+        opt_b.step()
+        opt_a.step()
+        assert abs(opt_a.total_norm().item() - norm_b.item()) <= 1e-4 * norm_b.item()
+        for (k, pa), pb in zip(a.named_parameters(), b.parameters()):
+            assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), (step, k)
+    sd = opt_a.state_dict()
+    ref = opt_b.state_dict()
+    assert sd["state"].keys() == ref["state"].keys()
+    assert float(sd["state"][0]["step"]) == 3.0
+    assert torch.allclose(sd["state"][0]["exp_inf"], ref["state"][0]["exp_inf"], rtol=1e-5, atol=1e-9)
