@@ -216,8 +216,7 @@ def run_ours(args):
         gl = model.nouns_loss(gt_pred_nouns, n)                # logged, never back-propagated (sr.py:70,76)
         (vl + nl).backward()
         flat.all_reduce()
-        torch.nn.utils.clip_grad_norm_(params, 1)               # sr.py:81
-        opt.step()
+        opt.step()                                              # clip_grad_norm_(1) + Adamax (sr.py:81-82)
         return torch.stack([vl.detach(), nl.detach(), gl.detach()])
 
     def barrier():

@@ -17,7 +17,8 @@ class GraphedTrainStep:
     Mirrors the body of the reference's training loop (sr.py:63-83) without AMP:
         zero grads; model(img, verb); verb_loss, nouns_loss, gt_nouns_loss; (verb_loss + nouns_loss).backward();
         [all-reduce]; clip_grad_norm_(params, clip); optimizer.step()
-    `optimizer` must be capturable (e.g. torch.optim.Adamax(..., capturable=True)).  Inputs may live on the host
+    `optimizer` must be capturable: parallel.FlatAdamax (fused clip + Adamax kernel) or
+    torch.optim.Adamax(..., capturable=True).  Inputs may live on the host
     (pinned) or on the device; they are copied into the graph's static buffers before each replay.
     """
 
@@ -45,8 +46,9 @@ class GraphedTrainStep:
         gl = m.nouns_loss(gt_pred_nouns, n)
         (vl + nl).backward()
         self.flat.all_reduce()
-        torch.nn.utils.clip_grad_norm_(self.params, self.clip)
-        self.opt.step()
+        if not getattr(self.opt, "fused_clip", False):
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+        self.opt.step()                         # FlatAdamax clips inside its fused kernel
         return torch.stack([vl.detach(), nl.detach(), gl.detach()])
 
     def capture(self, example):

@@ -102,7 +102,8 @@ class _Engine:
 
     def ensure_packed(self, model, prec):
         params = self.param_list(model)
-        key = (prec,) + tuple((p.data_ptr(), p._version) for p in params)
+        flat = getattr(model, "_flat", None)
+        key = (prec, getattr(flat, "version", 0)) + tuple((p.data_ptr(), p._version) for p in params)
         if key == self._packed_key:
             return
         for p in params:
@@ -364,6 +365,7 @@ class FCGGNN(nn.Module):
         import weakref
         self.ggsnn._owner = weakref.ref(self)
         self._engines = {}
+        self._flat = None                # parallel.attach(): flat gradient / parameter buffers
 
     # sr.py accesses model.module.* when CUDA is available (DataParallel wrapper in the reference)
     @property

@@ -45,14 +45,17 @@ class FlatGrads:
         return self.flat.numel() * self.flat.element_size()
 
 
-def attach(model, group=None):
-    """Make `model`'s losses use global denominators over `group` and return the FlatGrads of its trainable
-    parameters (call `.zero()` instead of `optimizer.zero_grad()`, `.all_reduce()` after `backward()`)."""
+def attach(model, group=None, flat_params=False):
+    """Make `model`'s losses use global denominators over `group` and return the FlatGrads (or, with
+    `flat_params=True`, the FlatParams needed by FlatAdamax) of its trainable parameters: call `.zero()` instead of
+    `optimizer.zero_grad()` and `.all_reduce()` after `backward()`."""
     if dist.is_available() and dist.is_initialized():
         model.loss_group = group if group is not None else dist.group.WORLD
     else:
         model.loss_group = None
-    return FlatGrads(model.parameters())
+    flat = FlatParams(model.parameters()) if flat_params else FlatGrads(model.parameters())
+    model._flat = flat
+    return flat
 
 
 class FlatParams(FlatGrads):
@@ -73,6 +76,7 @@ class FlatParams(FlatGrads):
                 p.data = view
                 off += p.numel()
         self.params = params
+        self.version = 0   # bumped by FlatAdamax.step(): raw kernels do not touch torch's tensor version counters
         self.flat = torch.zeros(n_pad, dtype=ref.dtype, device=ref.device)
         off = 0
         for p in params:
@@ -84,6 +88,8 @@ class FlatAdamax(torch.optim.Optimizer):
     """`clip_grad_norm_(params, max_norm)` + `torch.optim.Adamax` (sr.py:80-83,472-473) as ONE fused CUDA kernel over the
     flat buffers of `FlatParams` (srg_clip_adamax).  The per-parameter state (`step`, `exp_avg`, `exp_inf`) is exposed
     through the usual `state_dict()` so checkpoints stay interchangeable with torch.optim.Adamax."""
+
+    fused_clip = True   # the gradient clipping is part of step()
 
     def __init__(self, flat, lr=0.002, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
         if not isinstance(flat, FlatParams):
@@ -110,6 +116,7 @@ class FlatAdamax(torch.optim.Optimizer):
                                        _lib.ptr(self.exp_inf), self.flat.flat.numel(), g["lr"], g["betas"][0],
                                        g["betas"][1], g["eps"], g["max_norm"], _lib.ptr(self.scratch),
                                        _lib.stream_ptr()))
+        self.flat.version += 1     # the packed bf16 weights of the model are stale now
 
     def total_norm(self):
         """Gradient norm seen by the last step (before clipping), like the return value of clip_grad_norm_."""

@@ -321,3 +321,23 @@ def test_fused_clip_adamax_matches_torch(enc_syn):
     assert sd["state"].keys() == ref["state"].keys()
     assert float(sd["state"][0]["step"]) == 3.0
     assert torch.allclose(sd["state"][0]["exp_inf"], ref["state"][0]["exp_inf"], rtol=1e-5, atol=1e-9)
+
+
+def test_eager_steps_with_fused_optimizer_repack_weights(enc_syn):
+    """FlatAdamax updates the weights with a raw kernel: the engine must notice and repack its bf16 operands."""
+    from situation_recognition_b200 import parallel
+    B, D = 8, 256
+    torch.manual_seed(0)
+    m = S.FCGGNN(enc_syn, D, backbone=None).cuda().eval()
+    flat = parallel.attach(m, flat_params=True)
+    opt = parallel.FlatAdamax(flat, lr=0.05)
+    fv, fn, gt_verb, gt_nouns = [x.cuda() for x in make_batch(enc_syn, B, D, seed=2)]
+    losses = []
+    for _ in range(4):
+        flat.zero()
+        pv, pn, gpn = m(fv, gt_verb, img_nouns=fn)
+        loss = m.verb_loss(pv, gt_verb) + m.nouns_loss(pn, gt_nouns)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0] - 0.5          # the same batch is being fitted: stale operands would freeze the loss
