@@ -69,11 +69,13 @@ template <int EPI, bool F32>
 struct EpiTraits {
   static constexpr int kSlots = (EPI == EPI_STORE_BF16) ? (F32 ? 6 : 2)
                                 : (EPI == EPI_STORE_F32) ? 4
-                                : (EPI == EPI_ZR)        ? (F32 ? 6 : 5)
+                                : (EPI == EPI_ZR)        ? (F32 ? 6 : 4)
                                 : (EPI == EPI_H)         ? (F32 ? 7 : 4)
                                 : (EPI == EPI_LOGITS)    ? 4
                                 : (EPI == EPI_DH)        ? 6
-                                                         : 4;
+                                                         : 2;   // EPI_DRH
+  // bf16 training instantiations of the fused GRU epilogues run the software-pipelined path (epilogue_pipe.cuh)
+  static constexpr bool kPipe = !F32 && (EPI == EPI_ZR || EPI == EPI_H || EPI == EPI_DH || EPI == EPI_DRH);
 };
 
 template <int CG, int BLOCK_N, int EPI, bool F32>
@@ -186,6 +188,10 @@ __device__ __forceinline__ void load_bias8(const float* bias, int col, float sca
   b[0] = x.x * scale; b[1] = x.y * scale; b[2] = x.z * scale; b[3] = x.w * scale;
   b[4] = y.x * scale; b[5] = y.y * scale; b[6] = y.z * scale; b[7] = y.w * scale;
 }
+
+}  // namespace srg
+#include "epilogue_pipe.cuh"
+namespace srg {
 
 // ------------------------------------------------------------------------------------------------
 template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool F32>
@@ -381,6 +387,87 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
     int store_set = 0;  // ping-pong for pure store epilogues
     (void)in_bar; (void)in_phase; (void)store_set;
 
+    if constexpr (EpiTraits<EPI, F32>::kPipe) {
+      // ---------------------------------------------------------------- software-pipelined path (epilogue_pipe.cuh)
+      constexpr int NCH = BLOCK_N / 32;
+      constexpr int SETB = PipeTraits<EPI>::kSetBytes;
+      static_assert(NCH % 2 == 0, "ping-pong sets assume an even number of chunks per tile");
+      uint8_t* wsm = smem_epi + ew * (2 * SETB);
+      uint64_t* bar2 = &epi_in_bar[ew * 2];
+      const PipeCtx ctx{&maps, &args, wsm, bar2, lane};
+      auto row_of = [&](int w_) {
+        return ((w_ % tiles_mn) / num_n_tiles) * kTileM * CG + static_cast<int>(cta_rank) * kTileM + ew * 32;
+      };
+      auto n0_of = [&](int w_) { return ((w_ % tiles_mn) % num_n_tiles) * BLOCK_N; };
+      auto needs_in = [&](int n0_) { return EPI != EPI_ZR || n0_ >= args.n_split; };
+      int set = 0;
+      uint32_t ph = 0;
+      bool issued = false;   // the loads of the chunk about to be processed are already in flight
+      for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
+        const int row0 = row_of(w), n0 = n0_of(w);
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        const bool active = row0 < args.M;
+        const bool tin = needs_in(n0);
+        const bool r_tile = (EPI == EPI_ZR) && tin;
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+        if (!active) {
+          ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        } else {
+#pragma unroll 1
+          for (int cc = 0; cc < NCH; ++cc) {
+            uint8_t* sp = wsm + set * SETB;
+            // the chunk after this one: next chunk of the tile, or chunk 0 of this warp's next (active) tile
+            int nw = w, ncc = cc + 1;
+            bool nvalid = true;
+            if (ncc == NCH) {
+              nw = w + num_clusters;
+              ncc = 0;
+              nvalid = (nw < total_work) && (row_of(nw) < args.M);
+            }
+            const bool pre = nvalid && needs_in(n0_of(nw));
+            if (lane == 0 && tin && !issued) {   // only the first chunk of a run is not prefetched
+              ptx::tma_wait_group_read<0>();
+              pipe_issue<EPI>(ctx, sp, &bar2[set], n0, cc, row0);
+            }
+            if (cc == 0) {
+              ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+              ptx::tcgen05_fence_after();
+            }
+            if (tin) {
+              ptx::mbar_wait(&bar2[set], (ph >> set) & 1u);
+              ph ^= (1u << set);
+            }
+            if (lane == 0) {
+              if (pre) {     // the other set's last stores were committed one iteration ago
+                ptx::tma_wait_group_read<0>();
+                pipe_issue<EPI>(ctx, wsm + (set ^ 1) * SETB, &bar2[set ^ 1], n0_of(nw), ncc, row_of(nw));
+              } else {
+                ptx::tma_wait_group_read<1>();   // this set's stores of two chunks ago
+              }
+            }
+            issued = pre;
+            if (!tin) __syncwarp();              // output-only chunk: lanes must not overwrite the set before that wait
+            float accv[32];
+            ptx::tmem_ld_32x32(tacc + cc * 32, accv);
+            ptx::tmem_ld_wait();
+            pipe_compute<EPI>(ctx, ptx::smem_u32(sp), accv, n0, cc, r_tile);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              pipe_store<EPI>(ctx, sp, n0, cc, row0, r_tile);
+              ptx::tma_commit_group();
+            }
+            set ^= 1;
+          }
+        }
+        ptx::tcgen05_fence_before();
+        if constexpr (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      if (lane == 0) ptx::tma_wait_group<0>();
+      __syncwarp();
+    } else
     for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
       const int nt = (w % tiles_mn) % num_n_tiles;
       const int mt = (w % tiles_mn) / num_n_tiles;

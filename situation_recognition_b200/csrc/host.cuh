@@ -88,13 +88,14 @@ inline PFN_encodeTiled get_encode_fn() {
 enum DType : int { DT_NONE = 0, DT_F32 = 1, DT_BF16 = 2 };
 
 // Row-major 2-D tensor [rows, cols] with leading dimension `ld` (elements); box = [box_rows, box_cols];
-// SWIZZLE_128B (box_cols * elem_size must be 128 bytes).
+// SWIZZLE_128B when a box row spans 128 bytes, SWIZZLE_64B when it spans 64 bytes.
 inline int make_tmap(CUtensorMap* out, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld,
                      int box_rows, int box_cols) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(SRG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const int es = (dtype == DT_F32) ? 4 : 2;
-  SRG_CHECK(box_cols * es == 128, "TMA box must span 128 bytes (got %d)", box_cols * es);
+  SRG_CHECK(box_cols * es == 128 || box_cols * es == 64, "TMA box must span 128 or 64 bytes (got %d)", box_cols * es);
+  const CUtensorMapSwizzle swz = (box_cols * es == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   SRG_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer must be 16-byte aligned");
   SRG_CHECK(((ld * es) & 15) == 0, "TMA row pitch must be a multiple of 16 bytes (ld=%lld)", (long long)ld);
   SRG_CHECK(rows > 0 && cols > 0, "empty tensor for TMA (%lld x %lld)", (long long)rows, (long long)cols);
@@ -104,7 +105,7 @@ inline int make_tmap(CUtensorMap* out, const void* ptr, int dtype, int64_t rows,
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, dtype == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(SRG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r,
                      (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
@@ -313,8 +314,10 @@ inline int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t st
   bool have_io0 = false;
   for (int i = 0; i < kMaxIoMaps; ++i) {
     if (p.io[i].dtype == DT_NONE || p.io[i].ptr == nullptr) continue;
+    // the software-pipelined epilogues move 32-column chunks (bf16: 64-byte rows), the others 64-column chunks
+    const bool pipe = !p.f32 && (p.epi == EPI_ZR || p.epi == EPI_H || p.epi == EPI_DH || p.epi == EPI_DRH);
     SRG_TRY(make_tmap(&maps.io[i], p.io[i].ptr, p.io[i].dtype, p.io[i].rows, p.io[i].cols, p.io[i].ld, 32,
-                      io_box_cols(p.io[i].dtype)));
+                      pipe ? 32 : io_box_cols(p.io[i].dtype)));
     if (i == 0) have_io0 = true;
   }
   (void)have_io0;

@@ -168,6 +168,8 @@ class _NounsStage(torch.autograd.Function):
                                              prec, int(need_grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         if need_grad:
             ctx.eng, ctx.ws, ctx.B, ctx.drop_p = eng, ws, B, drop_p
+            ctx.direct = model._direct_grads()
+            ctx.live = (role_emb, verb_emb) + tuple(params)       # the Parameter objects (for .grad in direct mode)
             ctx.save_for_backward(feat, verb, keep, role_emb, verb_emb, *params)
         return logits.view(B, eng.R, eng.Lpad)[:, :, :eng.L]
 
@@ -177,14 +179,18 @@ class _NounsStage(torch.autograd.Function):
         feat, verb, keep, role_emb, verb_emb, *params = ctx.saved_tensors
         B = ctx.B
         dl, ldl = _padded_grad(dlogits.reshape(B * eng.R, eng.L), eng.Lpad)
-        grads = {n: torch.zeros_like(p) for n, p in zip(_GGNN_FIELDS + ["Wc_noun", "bc_noun"], params)}
-        grads["role_emb"] = torch.zeros_like(role_emb)
-        grads["verb_emb"] = torch.zeros_like(verb_emb)
+        names = ["role_emb", "verb_emb"] + _GGNN_FIELDS + ["Wc_noun", "bc_noun"]
+        if ctx.direct:   # flat-buffer mode: the kernels accumulate straight into the (pre-zeroed) .grad views
+            grads = {n: p.grad for n, p in zip(names, ctx.live)}
+        else:
+            grads = {n: torch.zeros_like(p) for n, p in zip(names, (role_emb, verb_emb) + tuple(params))}
         sg = _grad_struct(grads, eng)
         _lib.check(eng.lib.srg_nouns_backward(eng.h, _lib.ptr(dl), ldl, _lib.ptr(feat), _lib.ptr(verb), B,
                                               _lib.ptr(role_emb), _lib.ptr(verb_emb), _lib.ptr(keep), ctx.drop_p,
                                               ctypes.byref(sg), _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()))
         ctx.ws = None
+        if ctx.direct:
+            return (None,) * (5 + len(names))
         out = [grads[n] for n in _GGNN_FIELDS + ["Wc_noun", "bc_noun"]]
         return (None, None, None, None, None, grads["role_emb"], grads["verb_emb"], *out)
 
@@ -209,6 +215,8 @@ class _VerbStage(torch.autograd.Function):
                                             _lib.stream_ptr()))
         if need_grad:
             ctx.eng, ctx.ws, ctx.B, ctx.drop_p = eng, ws, B, drop_p
+            ctx.direct = model._direct_grads()
+            ctx.live = tuple(params)
             ctx.save_for_backward(keep, *params)
         return logits[:, :eng.V]
 
@@ -218,12 +226,18 @@ class _VerbStage(torch.autograd.Function):
         keep, *params = ctx.saved_tensors
         B = ctx.B
         dl, ldl = _padded_grad(dlogits.reshape(B, eng.V), eng.Vpad)
-        grads = {n: torch.zeros_like(p) for n, p in zip(_GGNN_FIELDS + ["Wc_verb", "bc_verb"], params)}
+        names = _GGNN_FIELDS + ["Wc_verb", "bc_verb"]
+        if ctx.direct:
+            grads = {n: p.grad for n, p in zip(names, ctx.live)}
+        else:
+            grads = {n: torch.zeros_like(p) for n, p in zip(names, params)}
         sg = _grad_struct(grads, eng)
         _lib.check(eng.lib.srg_verb_backward(eng.h, _lib.ptr(dl), ldl, B, _lib.ptr(keep), ctx.drop_p, ctypes.byref(sg),
                                              _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()))
         ctx.ws = None
-        return (None, None, None, None, *[grads[n] for n in _GGNN_FIELDS + ["Wc_verb", "bc_verb"]])
+        if ctx.direct:
+            return (None,) * (4 + len(names))
+        return (None, None, None, None, *[grads[n] for n in names])
 
 
 def _padded_grad(g, npad):
@@ -379,6 +393,14 @@ class FCGGNN(nn.Module):
             eng = _Engine(self, torch.device("cuda", key[1]))
             self._engines[key] = eng
         return eng
+
+    def _direct_grads(self):
+        """True when parallel.attach() installed flat gradient buffers: the backward kernels then accumulate into the
+        pre-zeroed `.grad` views directly (no per-tensor zero-fill and no autograd accumulation kernels)."""
+        flat = self._flat
+        if flat is None:
+            return False
+        return all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() for p in flat.params)
 
     def _ggnn_params(self):
         g = self.ggsnn
