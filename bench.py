@@ -265,10 +265,12 @@ def run_ours(args):
     fl_k = (ctypes.c_double * kinds)()
     ct_k = (ctypes.c_longlong * kinds)()
     barrier()
+    model.overlap_streams = False     # per-kernel event timing needs the kernels one after the other on one stream
     lib.srg_profile_begin()
     for _ in range(args.steps):
         step(resident)
     _lib.check(lib.srg_profile_end(kinds, ms_k, fl_k, ct_k))
+    model.overlap_streams = True
     peaks = load_peaks()
     per_kind = []
     for k in range(kinds):

@@ -641,7 +641,7 @@ __global__ void k_outer_acc(const float* __restrict__ sv, const float* __restric
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int o = static_cast<int>(t / cols), k = static_cast<int>(t % cols);
-    dW[t] += sv[o] * b[k];
+    atomicAdd(dW + t, sv[o] * b[k]);   // the verb and noun backward passes may run concurrently on two streams
   }
 }
 

@@ -379,6 +379,8 @@ class FCGGNN(nn.Module):
         import weakref
         self.ggsnn._owner = weakref.ref(self)
         self._engines = {}
+        self._side_streams = {}
+        self.overlap_streams = True      # run the verb path on a side stream (see forward)
         self._flat = None                # parallel.attach(): flat gradient / parameter buffers
 
     # sr.py accesses model.module.* when CUDA is available (DataParallel wrapper in the reference)
@@ -435,12 +437,32 @@ class FCGGNN(nn.Module):
 
     def forward(self, img, gt_verb, img_nouns=None):
         """model.py:171-180.  `img_nouns` (extension) lets benchmarks feed different synthetic features to the verb
-        and noun paths, as the two backbones would produce."""
+        and noun paths, as the two backbones would produce.
+
+        The verb path (B nodes) is small next to a noun path (6B nodes) and leaves most SMs idle, so it runs on a side
+        stream concurrently with the gt-verb noun path (which does not depend on it); the predicted-verb noun path
+        waits for it.  autograd replays the same streams, so the two backward passes overlap as well."""
         batch_size = img.size(0)
-        pred_verb = self.predict_verb(img, batch_size)
         img_n = img if img_nouns is None else img_nouns
-        pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1)
+        if not (self.overlap_streams and img.is_cuda):
+            pred_verb = self.predict_verb(img, batch_size)
+            pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1)
+            gt_pred_nouns = self.predict_nouns(img_n, gt_verb, batch_size, _mask_slot=2)
+            return pred_verb, pred_nouns, gt_pred_nouns
+        dev = img.device
+        cur = torch.cuda.current_stream(dev)
+        # the weights are packed once, before the fork, so both streams see the same operands
+        self._engine_for(dev).ensure_packed(self, _prec_code(self.precision))
+        side = self._side_streams.get(dev)
+        if side is None:
+            side = self._side_streams[dev] = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            pred_verb = self.predict_verb(img, batch_size)
         gt_pred_nouns = self.predict_nouns(img_n, gt_verb, batch_size, _mask_slot=2)
+        cur.wait_stream(side)
+        pred_verb.record_stream(cur)
+        pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1)
         return pred_verb, pred_nouns, gt_pred_nouns
 
     def verb_loss(self, pred_verb, gt_verb):
