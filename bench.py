@@ -193,12 +193,12 @@ def run_ours(args):
     model.train()
     if args.cta_group:
         model._engine_for(dev).set_cta_group(args.cta_group)
-    flat = parallel.attach(model)
+    flat = parallel.attach(model, flat_params=True)
     # kernels are launched eagerly by default: with the verb path overlapped on a side stream the GPU never waits for
     # the host (measured: graph replay 31.89 ms vs eager 31.87 ms at B=6144; 5.96 vs 5.84 ms at 8 x 768).  --graph
     # replays the whole step (NCCL all-reduce included) from one CUDA graph instead.
     use_graph = args.graph and not args.no_graph
-    opt = torch.optim.Adamax(model.parameters(), lr=0.002, capturable=use_graph)      # sr.py:472-473
+    opt = parallel.FlatAdamax(flat, lr=0.002, max_norm=1.0)      # sr.py:80-83,472-473 as one fused kernel
     params = [p for p in model.parameters() if p.requires_grad]
 
     Bg = args.batch

@@ -106,11 +106,18 @@ int srg_ggnn_forward(srg_handle* h, int mode, float* hidden, const float* mask, 
  * accumulated (+=).  dlogits: fp32 [B*R, ldl] or NULL; receives grad_scale * dLoss/dlogits (padding columns = 0). */
 int srg_count_targets(srg_handle* h, const int64_t* gt_nouns, int B, float* counts, void* stream);
 int srg_nouns_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_nouns, int B,
-                   const float* counts, float* loss, float* dlogits, float grad_scale, void* stream);
+                   const float* counts, float* loss, float* dlogits, float grad_scale, const float* stats,
+                   void* stream);
 
 /* FCGGNN.verb_loss (model.py:182-187): CrossEntropy(pred_verb[B, n_verbs], gt_verb[B]), mean over inv_batch = 1/B_global. */
 int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B, float inv_batch,
-                  float* loss, float* dlogits, float grad_scale, void* stream);
+                  float* loss, float* dlogits, float grad_scale, const float* stats, void* stream);
+
+/* `stats` (nullable) of the two loss calls: the per-column-tile (row max, row sum-exp) pairs the classifier GEMM of the
+ * matching forward call left in its workspace, at this byte offset; with them the loss reads each logits row once
+ * instead of three times.  They are only valid for the logits that forward call produced. */
+size_t srg_workspace_stats_offset(srg_handle* h, int mode, int B, int precision, int save_for_backward,
+                                  const void* workspace);
 
 /* autograd backward of srg_nouns_forward / srg_verb_forward (sr.py:76-79).  `workspace` must be the one used by the
  * matching forward call with save_for_backward = 1.  dlogits: fp32 [rows, ldl].  Gradients accumulate into `g`. */

@@ -694,6 +694,14 @@ int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* st
   return SRG_OK;
 }
 
+size_t srg_workspace_stats_offset(srg_handle* h, int mode, int B, int precision, int save_for_backward,
+                                  const void* workspace) {
+  if (!h || B <= 0 || !workspace) return 0;
+  // carve() only does pointer arithmetic; the offset depends on the alignment of the actual workspace address
+  PathBufs pb = carve(h, mode, B, precision, save_for_backward, const_cast<void*>(workspace));
+  return static_cast<size_t>(reinterpret_cast<const uint8_t*>(pb.stats) - static_cast<const uint8_t*>(workspace));
+}
+
 size_t srg_workspace_bytes(srg_handle* h, int mode, int B, int precision, int save_for_backward) {
   if (!h || B <= 0) return 0;
   return carve(h, mode, B, precision, save_for_backward, nullptr).bytes;
@@ -747,19 +755,20 @@ int srg_count_targets(srg_handle* h, const int64_t* gt_nouns, int B, float* coun
 }
 
 int srg_nouns_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_nouns, int B,
-                   const float* counts, float* loss, float* dlogits, float grad_scale, void* stream) {
+                   const float* counts, float* loss, float* dlogits, float grad_scale, const float* stats,
+                   void* stream) {
   SRG_CHECK(h && logits && gt_nouns && counts && loss, "srg_nouns_loss: null argument");
   SRG_CHECK(ldl >= h->L, "srg_nouns_loss: ldl %lld < n_labels %d", (long long)ldl, h->L);
-  return launch_nouns_ce(logits, ldl, h->L, gt_nouns, B, h->R, counts, loss, dlogits, grad_scale,
-                         static_cast<cudaStream_t>(stream));
+  return launch_nouns_ce(logits, ldl, h->L, gt_nouns, B, h->R, counts, loss, dlogits, grad_scale, stats,
+                         h->Lpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
 }
 
 int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B, float inv_batch,
-                  float* loss, float* dlogits, float grad_scale, void* stream) {
+                  float* loss, float* dlogits, float grad_scale, const float* stats, void* stream) {
   SRG_CHECK(h && logits && gt_verb && loss, "srg_verb_loss: null argument");
   SRG_CHECK(ldl >= h->V, "srg_verb_loss: ldl %lld < n_verbs %d", (long long)ldl, h->V);
-  return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, loss, dlogits, grad_scale,
-                        static_cast<cudaStream_t>(stream));
+  return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, loss, dlogits, grad_scale, stats,
+                        h->Vpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
 }
 
 int srg_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,

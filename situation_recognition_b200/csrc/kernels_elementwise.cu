@@ -299,7 +299,8 @@ template <int NT>
 __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, int n_classes, int rows,
                                 const int64_t* __restrict__ gt, int R, int ignore_index,
                                 const float* __restrict__ counts, float inv_fixed, float* __restrict__ loss,
-                                float* __restrict__ dlogits, float grad_scale) {
+                                float* __restrict__ dlogits, float grad_scale, const float2* __restrict__ stats,
+                                int stats_tiles) {
   __shared__ float s_loss[kThreads / 32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
@@ -322,12 +323,20 @@ __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, i
       wsum += w[a];
     }
     if (wsum == 0.f && dlogits == nullptr) continue;  // fully ignored row contributes nothing
-    float mx = -INFINITY;
-    for (int c = lane; c < n_classes; c += 32) mx = fmaxf(mx, lr[c]);
-    mx = warp_max(mx);
-    float se = 0.f;
-    for (int c = lane; c < n_classes; c += 32) se += __expf(lr[c] - mx);
-    se = warp_sum(se);
+    float mx = -INFINITY, se = 0.f;
+    if (stats != nullptr) {
+      // the classifier GEMM already reduced every 128/256-column tile of this row to (max, sum exp(x - max)):
+      // combine the per-tile pairs instead of reading the logits row two more times
+      float2 st = make_float2(-INFINITY, 0.f);
+      if (lane < stats_tiles) st = stats[static_cast<int64_t>(row) * stats_tiles + lane];
+      mx = warp_max(st.x);
+      se = warp_sum(st.y > 0.f ? st.y * __expf(st.x - mx) : 0.f);
+    } else {
+      for (int c = lane; c < n_classes; c += 32) mx = fmaxf(mx, lr[c]);
+      mx = warp_max(mx);
+      for (int c = lane; c < n_classes; c += 32) se += __expf(lr[c] - mx);
+      se = warp_sum(se);
+    }
     const float lse = mx + __logf(se);
     if (lane == 0) {
 #pragma unroll
@@ -830,24 +839,30 @@ int launch_count_targets(const int64_t* gt, int B, int R, int ignore_index, floa
 }
 
 int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_t* gt, int B, int R,
-                    const float* counts, float* loss, float* dlogits, float grad_scale, cudaStream_t s) {
+                    const float* counts, float* loss, float* dlogits, float grad_scale, const float* stats,
+                    int stats_tiles, cudaStream_t s) {
   const int rows = B * R;
   if (rows <= 0) return SRG_OK;
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (stats_tiles > 32) stats = nullptr;
   k_cross_entropy<3><<<blocks, kThreads, 0, s>>>(logits, ldl, n_labels, rows, gt, R, n_labels, counts, 0.f, loss,
-                                                dlogits, grad_scale);
+                                                dlogits, grad_scale, reinterpret_cast<const float2*>(stats),
+                                                stats_tiles);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
 int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t* gt, int B, float inv_batch,
-                   float* loss, float* dlogits, float grad_scale, cudaStream_t s) {
+                   float* loss, float* dlogits, float grad_scale, const float* stats, int stats_tiles,
+                   cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   int blocks = (B + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (stats_tiles > 32) stats = nullptr;
   k_cross_entropy<1><<<blocks, kThreads, 0, s>>>(logits, ldl, n_verbs, B, gt, 1, -100, nullptr, inv_batch, loss,
-                                                dlogits, grad_scale);
+                                                dlogits, grad_scale, reinterpret_cast<const float2*>(stats),
+                                                stats_tiles);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }

@@ -118,6 +118,12 @@ class _Engine:
         return torch.empty(n, dtype=torch.uint8, device=self.device)
 
 
+def _stats_view(eng, ws, mode, B, prec, save):
+    """(workspace tensor, device pointer) of the per-tile softmax statistics the classifier GEMM left in `ws`."""
+    off = eng.lib.srg_workspace_stats_offset(eng.h, mode, B, prec, int(save), _lib.ptr(ws))
+    return ws, ws.data_ptr() + off
+
+
 def _prec_code(name):
     if name in ("bf16", SRG_PREC_BF16):
         return SRG_PREC_BF16
@@ -171,6 +177,7 @@ class _NounsStage(torch.autograd.Function):
             ctx.direct = model._direct_grads()
             ctx.live = (role_emb, verb_emb) + tuple(params)       # the Parameter objects (for .grad in direct mode)
             ctx.save_for_backward(feat, verb, keep, role_emb, verb_emb, *params)
+        model._last_stats = _stats_view(eng, ws, SRG_MODE_NOUN, B, prec, need_grad)
         return logits.view(B, eng.R, eng.Lpad)[:, :, :eng.L]
 
     @staticmethod
@@ -218,6 +225,7 @@ class _VerbStage(torch.autograd.Function):
             ctx.direct = model._direct_grads()
             ctx.live = tuple(params)
             ctx.save_for_backward(keep, *params)
+        model._last_stats = _stats_view(eng, ws, SRG_MODE_VERB, B, prec, need_grad)
         return logits[:, :eng.V]
 
     @staticmethod
@@ -274,9 +282,11 @@ class _NounsLoss(torch.autograd.Function):
     """FCGGNN.nouns_loss (model.py:189-201): forward computes the loss and d(loss)/d(logits) in one pass."""
 
     @staticmethod
-    def forward(ctx, model, grad_on, logits, gt_nouns):
+    def forward(ctx, model, grad_on, logits, gt_nouns, stats_ptr):
         eng = model._engine_for(logits.device)
         x, rows, ld = _rows_view(logits, eng.L)
+        if x.data_ptr() != logits.data_ptr():
+            stats_ptr = None                       # the logits were copied / converted: the statistics do not apply
         B = rows // eng.R
         gt = gt_nouns.detach().to(torch.int64).contiguous()
         counts = torch.empty(3, dtype=torch.float32, device=logits.device)
@@ -287,7 +297,8 @@ class _NounsLoss(torch.autograd.Function):
         need_grad = grad_on and ctx.needs_input_grad[2]
         dl = torch.empty(rows, ld, dtype=torch.float32, device=logits.device) if need_grad else None
         _lib.check(eng.lib.srg_nouns_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts), _lib.ptr(loss),
-                                          _lib.ptr(dl), 1.0, _lib.stream_ptr()))
+                                          _lib.ptr(dl), 1.0, ctypes.c_void_p(stats_ptr) if stats_ptr else None,
+                                          _lib.stream_ptr()))
         if need_grad:
             ctx.save_for_backward(dl)
             ctx.shape = tuple(logits.shape)
@@ -298,16 +309,18 @@ class _NounsLoss(torch.autograd.Function):
     def backward(ctx, gout):
         (dl,) = ctx.saved_tensors
         g = dl if _is_one(gout) else dl * gout
-        return None, None, g[:, :ctx.n].view(ctx.shape), None
+        return None, None, g[:, :ctx.n].view(ctx.shape), None, None
 
 
 class _VerbLoss(torch.autograd.Function):
     """FCGGNN.verb_loss (model.py:182-187)."""
 
     @staticmethod
-    def forward(ctx, model, grad_on, logits, gt_verb):
+    def forward(ctx, model, grad_on, logits, gt_verb, stats_ptr):
         eng = model._engine_for(logits.device)
         x, rows, ld = _rows_view(logits, eng.V)
+        if x.data_ptr() != logits.data_ptr():
+            stats_ptr = None
         gt = gt_verb.detach().to(torch.int64).contiguous()
         world = 1
         if model.loss_group is not None:
@@ -316,7 +329,8 @@ class _VerbLoss(torch.autograd.Function):
         need_grad = grad_on and ctx.needs_input_grad[2]
         dl = torch.empty(rows, ld, dtype=torch.float32, device=logits.device) if need_grad else None
         _lib.check(eng.lib.srg_verb_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, 1.0 / (rows * world),
-                                         _lib.ptr(loss), _lib.ptr(dl), 1.0, _lib.stream_ptr()))
+                                         _lib.ptr(loss), _lib.ptr(dl), 1.0,
+                                         ctypes.c_void_p(stats_ptr) if stats_ptr else None, _lib.stream_ptr()))
         if need_grad:
             ctx.save_for_backward(dl)
             ctx.shape = tuple(logits.shape)
@@ -327,11 +341,17 @@ class _VerbLoss(torch.autograd.Function):
     def backward(ctx, gout):
         (dl,) = ctx.saved_tensors
         g = dl if _is_one(gout) else dl * gout
-        return None, None, g[:, :ctx.n].view(ctx.shape), None
+        return None, None, g[:, :ctx.n].view(ctx.shape), None, None
 
 
 def _is_one(g):
     return False  # keep the general path; a fused scale is a later optimisation
+
+
+def _has_batchnorm_in_train(module):
+    """A backbone whose BatchNorm layers are in training mode updates its running statistics on every call; calling
+    it once instead of twice would change those statistics, so the dedupe is skipped in that case."""
+    return any(isinstance(m, nn.modules.batchnorm._BatchNorm) and m.training for m in module.modules())
 
 
 class GGSNN(nn.Module):
@@ -382,6 +402,7 @@ class FCGGNN(nn.Module):
         self._side_streams = {}
         self.overlap_streams = True      # run the verb path on a side stream (see forward)
         self._flat = None                # parallel.attach(): flat gradient / parameter buffers
+        self._last_stats = None
 
     # sr.py accesses model.module.* when CUDA is available (DataParallel wrapper in the reference)
     @property
@@ -418,22 +439,29 @@ class FCGGNN(nn.Module):
         return torch.empty(rows, self.D, dtype=torch.uint8, device=device).bernoulli_(1.0 - self.drop_p)
 
     # ---- reference API -------------------------------------------------------------------------
-    def predict_nouns(self, img, gt_verb, batch_size, _mask_slot=1):
-        feat = _as_feat(self.convnet_nouns(img), self.D)
+    def predict_nouns(self, img, gt_verb, batch_size, _mask_slot=1, _feat=None):
+        # `_feat`: backbone features computed once by forward() for both noun passes (the reference runs the frozen
+        # convnet_nouns twice on the same images, model.py:116,176-178)
+        feat = _feat if _feat is not None else _as_feat(self.convnet_nouns(img), self.D)
         if feat.shape[0] != batch_size:
             raise _lib.SrgError("batch_size %d does not match the features (%d)" % (batch_size, feat.shape[0]))
         keep = self._keep_mask(_mask_slot, batch_size * self.encoder.get_max_role_count(), feat.device)
         gt_verb = gt_verb.to(feat.device)
-        return _NounsStage.apply(self, torch.is_grad_enabled(), feat, gt_verb, keep, self.role_emb.weight, self.verb_emb.weight,
-                                 *self._ggnn_params(), self.nouns_classifier[1].weight, self.nouns_classifier[1].bias)
+        out = _NounsStage.apply(self, torch.is_grad_enabled(), feat, gt_verb, keep, self.role_emb.weight,
+                                self.verb_emb.weight, *self._ggnn_params(), self.nouns_classifier[1].weight,
+                                self.nouns_classifier[1].bias)
+        out._srg_stats = self._last_stats      # lets nouns_loss() reuse the classifier's per-tile softmax statistics
+        return out
 
     def predict_verb(self, img, batch_size):
         feat = _as_feat(self.convnet_verbs(img), self.D)
         if feat.shape[0] != batch_size:
             raise _lib.SrgError("batch_size %d does not match the features (%d)" % (batch_size, feat.shape[0]))
         keep = self._keep_mask(0, batch_size, feat.device)
-        return _VerbStage.apply(self, torch.is_grad_enabled(), feat, keep, *self._ggnn_params(), self.verb_classifier[1].weight,
-                                self.verb_classifier[1].bias)
+        out = _VerbStage.apply(self, torch.is_grad_enabled(), feat, keep, *self._ggnn_params(),
+                               self.verb_classifier[1].weight, self.verb_classifier[1].bias)
+        out._srg_stats = self._last_stats
+        return out
 
     def forward(self, img, gt_verb, img_nouns=None):
         """model.py:171-180.  `img_nouns` (extension) lets benchmarks feed different synthetic features to the verb
@@ -444,10 +472,14 @@ class FCGGNN(nn.Module):
         waits for it.  autograd replays the same streams, so the two backward passes overlap as well."""
         batch_size = img.size(0)
         img_n = img if img_nouns is None else img_nouns
+        # the noun backbone is frozen and deterministic in eval mode: evaluate it once for both noun passes
+        feat_n = None
+        if img_n.is_cuda and not (self.training and _has_batchnorm_in_train(self.convnet_nouns)):
+            feat_n = _as_feat(self.convnet_nouns(img_n), self.D)
         if not (self.overlap_streams and img.is_cuda):
             pred_verb = self.predict_verb(img, batch_size)
-            pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1)
-            gt_pred_nouns = self.predict_nouns(img_n, gt_verb, batch_size, _mask_slot=2)
+            pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1, _feat=feat_n)
+            gt_pred_nouns = self.predict_nouns(img_n, gt_verb, batch_size, _mask_slot=2, _feat=feat_n)
             return pred_verb, pred_nouns, gt_pred_nouns
         dev = img.device
         cur = torch.cuda.current_stream(dev)
@@ -459,17 +491,31 @@ class FCGGNN(nn.Module):
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             pred_verb = self.predict_verb(img, batch_size)
-        gt_pred_nouns = self.predict_nouns(img_n, gt_verb, batch_size, _mask_slot=2)
+        gt_pred_nouns = self.predict_nouns(img_n, gt_verb, batch_size, _mask_slot=2, _feat=feat_n)
         cur.wait_stream(side)
         pred_verb.record_stream(cur)
-        pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1)
+        pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1, _feat=feat_n)
         return pred_verb, pred_nouns, gt_pred_nouns
 
+    @staticmethod
+    def _stats_ptr(logits, expected_rows_stride):
+        """Device pointer of the classifier's per-tile softmax statistics if `logits` is the very tensor a predict_*
+        call of this model returned (same storage, same layout), else None."""
+        st = getattr(logits, "_srg_stats", None)
+        if st is None or logits.dtype != torch.float32 or logits.stride(-1) != 1 or \
+                logits.stride(-2) != expected_rows_stride:
+            return None
+        return st[1]
+
     def verb_loss(self, pred_verb, gt_verb):
-        return _VerbLoss.apply(self, torch.is_grad_enabled(), pred_verb, gt_verb.to(pred_verb.device))
+        eng_pad = _pad256(self.encoder.get_num_verbs())
+        return _VerbLoss.apply(self, torch.is_grad_enabled(), pred_verb, gt_verb.to(pred_verb.device),
+                               self._stats_ptr(pred_verb, eng_pad) if pred_verb.dim() == 2 else None)
 
     def nouns_loss(self, pred_nouns, gt_nouns):
-        return _NounsLoss.apply(self, torch.is_grad_enabled(), pred_nouns, gt_nouns.to(pred_nouns.device))
+        eng_pad = _pad256(self.encoder.get_num_labels())
+        return _NounsLoss.apply(self, torch.is_grad_enabled(), pred_nouns, gt_nouns.to(pred_nouns.device),
+                                self._stats_ptr(pred_nouns, eng_pad) if pred_nouns.dim() == 3 else None)
 
     # ---- GGSNN.forward drop-in (inference) ------------------------------------------------------
     def _ggsnn_forward(self, hidden_state, mask=None, verb=False):
