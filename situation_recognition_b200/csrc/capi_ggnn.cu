@@ -371,7 +371,7 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
 
   // dL/dh' of the last step comes from the classifier; from there on the GRU-gate derivatives of step t-1 are fused
   // into the epilogue of the GEMM that completes dL/dh of step t (EPI_DH).
-  // dpre[cur] = [dpre_h | dpre_z | dpre_r] as column blocks of one [M, 3D] matrix.
+  // dpre_of(t) = [dpre_h | dpre_z | dpre_r] of step t as column blocks of one [M, 3D] matrix.
   float* dh_acc = pb.dh_acc;
   auto dpre_of = [&](int t) { return pb.dpre_all + static_cast<size_t>(t) * M * ld3; };
   SRG_TRY(launch_gru_bwd_pre_ld(pb.dh, static_cast<const bf16*>(pb.st[T - 1].z), pb.st[T - 1].hc, pb.hb_hi[T - 1], M, D,
@@ -379,9 +379,7 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
   for (int t = T - 1; t >= 0; --t) {
     StepBufs& st = pb.st[t];
     bf16* dp = dpre_of(t);
-    bf16* dpre_h = dp;
-    bf16* dpre_z = dp + D;
-    bf16* dpre_r = dp + 2 * D;
+    bf16* dpre_r = dp + 2 * D;   // column blocks of dp: [dpre_h | dpre_z | dpre_r]
     {  // d(r*h) = dpre_h U_h ; fused: dpre_r = drh*h*r*(1-r), e = drh*r (this path's share of dL/dh)
       GemmProblem p = base_problem(h, M, D);
       add_seg_ld(p, dp, M, ld3, ld3, 0, D);

@@ -26,14 +26,9 @@ int launch_split_cast(const float* x, int64_t n, bf16* hi, bf16* mid, bf16* lo, 
 // a[b,i,:] = sum_j mask[b,i,j] * h[b,j,:]    (model.py:67-75 with the projection hoisted out of the sum)
 int launch_aggregate(const float* h32, const float* mask, int B, int R, int D, bf16* a_hi, bf16* a_mid, bf16* a_lo,
                      cudaStream_t s);
-// dh[b,j,:] = dh_acc[b,j,:] + sum_i mask[b,i,j] * da[b,i,:]
-int launch_aggregate_bwd(const float* dh_acc, const float* da, const float* mask, int B, int R, int D, float* dh,
-                         cudaStream_t s);
 
-// dst[r, col_off + c] = bf16 part `want_lo` (0 hi, 1 mid, 2 lo) of src[r, c] (r < rows), 0 for rows <= r < rows_pad
-int launch_pack_weight(const float* src, int rows, int cols, int rows_pad, bf16* dst, int64_t ld_dst, int64_t col_off,
-                       int want_lo, cudaStream_t s);
-// many pack_weight jobs in one launch (all with `cols` columns)
+// dst[r, col_off + c] = bf16 part `part` (0 hi, 1 mid, 2 lo) of src[r, c] (r < rows), 0 for rows <= r < rows_pad;
+// many such jobs in one launch (all with `cols` columns)
 struct PackJob {
   const float* src;
   bf16* dst;
@@ -62,9 +57,6 @@ int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t*
 // fp32 [rows, ld] (first n_valid columns) -> bf16 [rows, n_pad], zero padded
 int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, cudaStream_t s);
 
-// GRU backward prologue:  dpre_z = dh'*(hc-h)*z*(1-z), dpre_h = dh'*z*(1-hc^2), dh_acc = dh'*(1-z)
-int launch_gru_bwd_pre(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int64_t n, bf16* dpre_z,
-                       bf16* dpre_h, float* dh_acc, cudaStream_t s);
 // out1[c] (+= scale1 * colsum) , out2[c] (+= scale2 * colsum); X bf16 [rows, ld], first n_cols columns
 int launch_colsum(const bf16* X, int64_t ld, int rows, int n_cols, float* out1, float scale1, float* out2,
                   float scale2, cudaStream_t s);
@@ -87,7 +79,6 @@ struct ColsumJob {
 };
 int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows, int n_cols, cudaStream_t s);
 
-int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s);
 
 // clip_grad_norm_(max_norm) + Adamax on flat fp32 buffers (sr.py:80-83).  scratch: device fp32 [2] = {sum g^2, step}.
 int launch_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,

@@ -380,9 +380,6 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
     auto slot_ptr = [&](int i) -> void* { return smem_epi + (ew * SLOTS + i) * kSlotBytes; };
     uint64_t* in_bar = &epi_in_bar[ew * 2];
     uint32_t in_phase = 0;
-    uint32_t in_phase2 = 0;    // EPI_DRH: phase bits of the two ping-pong input sets
-    bool pre_issued = false;   // EPI_DRH: the loads of the coming tile's first chunk are already in flight
-    (void)in_phase2; (void)pre_issued;
     int iter = 0;
     int store_set = 0;  // ping-pong for pure store epilogues
     (void)in_bar; (void)in_phase; (void)store_set;
@@ -733,147 +730,6 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
                 ptx::tma_store_2d(&maps.io[5], slot_ptr(S_HL), gcol, row0);
               }
               else if (args.flags & FLAG_STASH) ptx::tma_store_2d(&maps.io[4], slot_ptr(S_Z), gcol, row0);
-            }
-            ptx::tma_commit_group();
-          }
-        } else if constexpr (EPI == EPI_DRH) {
-          // backward of rh = r*h:  drh = acc.
-          //   io0 = h (bf16 in), io1 = r (bf16 in); io2 = dpre_r (bf16 out) = drh*h*r*(1-r), io3 = e (bf16 out) = drh*r
-          //   (e is the contribution of this path to dL/dh; it is added when dL/dh is completed, EPI_DH).
-          // Both outputs overwrite their inputs in shared memory, so a chunk needs two slots; two sets ping-pong and
-          // the loads of the NEXT chunk (of this tile or of the warp's next tile) are issued before this one is
-          // processed, which takes the TMA load latency off the critical path of this short-K GEMM.
-          constexpr int NCH = BLOCK_N / 64;
-          static_assert(NCH % 2 == 0, "ping-pong sets assume an even number of column chunks per tile");
-          const int set = cc & 1;
-          auto issue = [&](int st, int col, int row) {
-            ptx::mbar_arrive_expect_tx(&in_bar[st], 2 * kSlotBytes);
-            ptx::tma_load_2d(&maps.io[0], &in_bar[st], slot_ptr(2 * st), col, row);
-            ptx::tma_load_2d(&maps.io[1], &in_bar[st], slot_ptr(2 * st + 1), col, row);
-          };
-          if (lane == 0) {
-            if (cc == 0 && !pre_issued) {
-              ptx::tma_wait_group_read<0>();
-              issue(0, gcol, row0);
-            }
-            // next chunk in sequence -> the other set (its previous stores were committed one iteration ago)
-            if (cc + 1 < NCH) {
-              ptx::tma_wait_group_read<0>();
-              issue(set ^ 1, gcol + 64, row0);
-            } else {
-              const int w2 = w + num_clusters;
-              if (w2 < total_work) {
-                const int nt2 = (w2 % tiles_mn) % num_n_tiles, mt2 = (w2 % tiles_mn) / num_n_tiles;
-                const int row2 = mt2 * kTileM * CG + static_cast<int>(cta_rank) * kTileM + ew * 32;
-                if (row2 < args.M) {
-                  ptx::tma_wait_group_read<0>();
-                  issue(set ^ 1, nt2 * BLOCK_N, row2);
-                }
-              }
-            }
-          }
-          if (cc + 1 == NCH) {  // warp-uniform copy of the decision taken by lane 0 above
-            const int w2 = w + num_clusters;
-            pre_issued = false;
-            if (w2 < total_work) {
-              const int mt2 = (w2 % tiles_mn) / num_n_tiles;
-              pre_issued = (mt2 * kTileM * CG + static_cast<int>(cta_rank) * kTileM + ew * 32) < args.M;
-            }
-          }
-          ptx::mbar_wait(&in_bar[set], (in_phase2 >> set) & 1u);
-          in_phase2 ^= (1u << set);
-          const uint32_t s_h = slot(2 * set), s_r = slot(2 * set + 1);
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            load_acc(cc * 64 + half * 32, accv);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float h[8], r[8], e[8], dp[8];
-              slot_ld_bf16x8(s_h, lane, half * 4 + g, h);
-              slot_ld_bf16x8(s_r, lane, half * 4 + g, r);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float d = accv[g * 8 + i];
-                dp[i] = d * h[i] * r[i] * (1.0f - r[i]);
-                e[i] = d * r[i];
-              }
-              slot_st_bf16x8(s_h, lane, half * 4 + g, dp);
-              slot_st_bf16x8(s_r, lane, half * 4 + g, e);
-            }
-          }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::tma_store_2d(&maps.io[2], slot_ptr(2 * set), gcol, row0);
-            ptx::tma_store_2d(&maps.io[3], slot_ptr(2 * set + 1), gcol, row0);
-            ptx::tma_commit_group();
-          }
-        } else if constexpr (EPI == EPI_DH) {
-          // g = acc + dh_acc is the gradient w.r.t. the state entering this step = the output of step t-1.
-          //   io0 = dh_acc fp32 (read-modify-write in place)
-          // FLAG_NEXT (t > 0): also apply the GRU update derivative of step t-1 in the same pass:
-          //   io1 = z, io2 = hc, io3 = h (bf16, step t-1);  io4 = dpre_z out, io5 = dpre_h out (bf16)
-          //   dpre_z = g*(hc-h)*z*(1-z), dpre_h = g*z*(1-hc^2), dh_acc = g*(1-z)
-          // FLAG_ADD: io6 = extra bf16 addend (the aggregated message gradient): g += add
-          constexpr int S_DH = 0, S_Z = 2, S_HC = 3, S_H = 4, S_ADD = 5;
-          const bool next = (args.flags & FLAG_NEXT) != 0;
-          const bool has_add = (args.flags & FLAG_ADD) != 0;
-          if (lane == 0) {
-            ptx::tma_wait_group_read<0>();
-            ptx::mbar_arrive_expect_tx(in_bar, (2 + (next ? 3 : 0) + (has_add ? 1 : 0)) * kSlotBytes);
-            ptx::tma_load_2d(&maps.io[0], in_bar, slot_ptr(S_DH), gcol, row0);
-            ptx::tma_load_2d(&maps.io[0], in_bar, slot_ptr(S_DH + 1), gcol + 32, row0);
-            if (has_add) ptx::tma_load_2d(&maps.io[6], in_bar, slot_ptr(S_ADD), gcol, row0);
-            if (next) {
-              ptx::tma_load_2d(&maps.io[1], in_bar, slot_ptr(S_Z), gcol, row0);
-              ptx::tma_load_2d(&maps.io[2], in_bar, slot_ptr(S_HC), gcol, row0);
-              ptx::tma_load_2d(&maps.io[3], in_bar, slot_ptr(S_H), gcol, row0);
-            }
-          }
-          ptx::mbar_wait(in_bar, in_phase);
-          in_phase ^= 1u;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            load_acc(cc * 64 + half * 32, accv);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float dh[8];
-              slot_ld_f32x8(slot(S_DH + half), lane, g, dh);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) dh[i] += accv[g * 8 + i];
-              if (has_add) {
-                float ad[8];
-                slot_ld_bf16x8(slot(S_ADD), lane, half * 4 + g, ad);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) dh[i] += ad[i];
-              }
-              if (next) {
-                float z[8], hc[8], h[8], dz[8], dc[8];
-                slot_ld_bf16x8(slot(S_Z), lane, half * 4 + g, z);
-                slot_ld_bf16x8(slot(S_HC), lane, half * 4 + g, hc);
-                slot_ld_bf16x8(slot(S_H), lane, half * 4 + g, h);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  dz[i] = dh[i] * (hc[i] - h[i]) * z[i] * (1.0f - z[i]);
-                  dc[i] = dh[i] * z[i] * (1.0f - hc[i] * hc[i]);
-                  dh[i] = dh[i] * (1.0f - z[i]);
-                }
-                slot_st_bf16x8(slot(S_Z), lane, half * 4 + g, dz);
-                slot_st_bf16x8(slot(S_HC), lane, half * 4 + g, dc);
-              }
-              slot_st_f32x8(slot(S_DH + half), lane, g, dh);
-            }
-          }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (warp_active) {
-              ptx::tma_store_2d(&maps.io[0], slot_ptr(S_DH), gcol, row0);
-              ptx::tma_store_2d(&maps.io[0], slot_ptr(S_DH + 1), gcol + 32, row0);
-              if (next) {
-                ptx::tma_store_2d(&maps.io[4], slot_ptr(S_Z), gcol, row0);
-                ptx::tma_store_2d(&maps.io[5], slot_ptr(S_HC), gcol, row0);
-              }
             }
             ptx::tma_commit_group();
           }

@@ -149,58 +149,7 @@ __global__ void k_aggregate(const float* __restrict__ h32, const float* __restri
   }
 }
 
-__global__ void k_aggregate_bwd(const float* __restrict__ dh_acc, const float* __restrict__ da,
-                                const float* __restrict__ mask, int B, int R, int D, float* __restrict__ dh) {
-  const int D4 = D / 4;
-  const int64_t total = static_cast<int64_t>(B) * D4;
-  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(t / D4);
-    const int d = static_cast<int>(t % D4) * 4;
-    float4 g[kMaxR];
-#pragma unroll
-    for (int i = 0; i < kMaxR; ++i)
-      if (i < R) g[i] = *reinterpret_cast<const float4*>(da + (static_cast<int64_t>(b) * R + i) * D + d);
-    const float* mb = mask + static_cast<int64_t>(b) * R * R;
-#pragma unroll
-    for (int j = 0; j < kMaxR; ++j) {
-      if (j < R) {
-        const int64_t off = (static_cast<int64_t>(b) * R + j) * D + d;
-        float4 a = *reinterpret_cast<const float4*>(dh_acc + off);
-#pragma unroll
-        for (int i = 0; i < kMaxR; ++i) {
-          if (i < R) {
-            const float m = __ldg(mb + i * R + j);
-            a.x = fmaf(m, g[i].x, a.x); a.y = fmaf(m, g[i].y, a.y);
-            a.z = fmaf(m, g[i].z, a.z); a.w = fmaf(m, g[i].w, a.w);
-          }
-        }
-        *reinterpret_cast<float4*>(dh + off) = a;
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ packing
-__global__ void k_pack_weight(const float* __restrict__ src, int rows, int cols, int rows_pad, bf16* __restrict__ dst,
-                              int64_t ld_dst, int64_t col_off, int want_lo) {
-  const int c2 = cols / 2;
-  const int64_t total = static_cast<int64_t>(rows_pad) * c2;
-  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(t / c2);
-    const int c = static_cast<int>(t % c2) * 2;
-    float2 v = make_float2(0.f, 0.f);
-    if (r < rows) v = *reinterpret_cast<const float2*>(src + static_cast<int64_t>(r) * cols + c);
-    for (int k = 0; k < want_lo; ++k) {   // want_lo = 0: hi part, 1: mid residual, 2: lo residual
-      v.x -= bf16_round(v.x);
-      v.y -= bf16_round(v.y);
-    }
-    *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<int64_t>(r) * ld_dst + col_off + c) =
-        __floats2bfloat162_rn(v.x, v.y);
-  }
-}
-
 struct PackJobs {
   PackJob j[kMaxPackJobs];
 };
@@ -384,32 +333,6 @@ __global__ void k_cast_pad(const float* __restrict__ src, int64_t ld, int rows, 
 }
 
 // ------------------------------------------------------------------------------------------------ GRU backward
-__global__ void k_gru_bwd_pre(const float* __restrict__ dh, const bf16* __restrict__ z, const bf16* __restrict__ hc,
-                              const bf16* __restrict__ h, int64_t n4, bf16* __restrict__ dpre_z,
-                              bf16* __restrict__ dpre_h, float* __restrict__ dh_acc) {
-  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float4 g = *reinterpret_cast<const float4*>(dh + t * 4);
-    const uint2 zz = *reinterpret_cast<const uint2*>(z + t * 4);
-    const uint2 cc = *reinterpret_cast<const uint2*>(hc + t * 4);
-    const uint2 hh = *reinterpret_cast<const uint2*>(h + t * 4);
-    const float gv[4] = {g.x, g.y, g.z, g.w};
-    const float zv[4] = {bf16_lo_f(zz.x), bf16_hi_f(zz.x), bf16_lo_f(zz.y), bf16_hi_f(zz.y)};
-    const float cv[4] = {bf16_lo_f(cc.x), bf16_hi_f(cc.x), bf16_lo_f(cc.y), bf16_hi_f(cc.y)};
-    const float hv[4] = {bf16_lo_f(hh.x), bf16_hi_f(hh.x), bf16_lo_f(hh.y), bf16_hi_f(hh.y)};
-    float dz[4], dc[4], da[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      dz[i] = gv[i] * (cv[i] - hv[i]) * zv[i] * (1.f - zv[i]);
-      dc[i] = gv[i] * zv[i] * (1.f - cv[i] * cv[i]);
-      da[i] = gv[i] * (1.f - zv[i]);
-    }
-    *reinterpret_cast<uint2*>(dpre_z + t * 4) = pack4_bf16(dz[0], dz[1], dz[2], dz[3]);
-    *reinterpret_cast<uint2*>(dpre_h + t * 4) = pack4_bf16(dc[0], dc[1], dc[2], dc[3]);
-    *reinterpret_cast<float4*>(dh_acc + t * 4) = make_float4(da[0], da[1], da[2], da[3]);
-  }
-}
-
 // column sums of a bf16 matrix; block = 8 warps x 64 columns, grid = (col chunks, row slabs)
 __global__ void k_colsum(const bf16* __restrict__ X, int64_t ld, int rows, int n_cols, float* __restrict__ out1,
                          float scale1, float* __restrict__ out2, float scale2) {
@@ -717,12 +640,6 @@ __global__ void k_clip_adamax(float* __restrict__ p, float* __restrict__ g, floa
 
 __global__ void k_inc(float* x) { *x += 1.0f; }
 
-__global__ void k_fill_f32(float* p, int64_t n, float v) {
-  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    p[t] = v;
-}
-
 #define SRG_LAUNCH_CHECK()                                                                      \
   do {                                                                                          \
     g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
@@ -775,23 +692,6 @@ int launch_aggregate(const float* h32, const float* mask, int B, int R, int D, b
   if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
   k_aggregate<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(h32, mask, B, R, D, a_hi,
                                                                              Parts{a_mid, a_lo});
-  SRG_LAUNCH_CHECK();
-  return SRG_OK;
-}
-
-int launch_aggregate_bwd(const float* dh_acc, const float* da, const float* mask, int B, int R, int D, float* dh,
-                         cudaStream_t s) {
-  if (B <= 0) return SRG_OK;
-  if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
-  k_aggregate_bwd<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(dh_acc, da, mask, B, R, D, dh);
-  SRG_LAUNCH_CHECK();
-  return SRG_OK;
-}
-
-int launch_pack_weight(const float* src, int rows, int cols, int rows_pad, bf16* dst, int64_t ld_dst, int64_t col_off,
-                       int want_lo, cudaStream_t s) {
-  k_pack_weight<<<grid_for(static_cast<int64_t>(rows_pad) * cols / 2), kThreads, 0, s>>>(src, rows, cols, rows_pad,
-                                                                                        dst, ld_dst, col_off, want_lo);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
@@ -870,14 +770,6 @@ int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t*
 int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, cudaStream_t s) {
   if (rows <= 0) return SRG_OK;
   k_cast_pad<<<grid_for(static_cast<int64_t>(rows) * n_pad / 2), kThreads, 0, s>>>(src, ld, rows, n_valid, n_pad, dst);
-  SRG_LAUNCH_CHECK();
-  return SRG_OK;
-}
-
-int launch_gru_bwd_pre(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int64_t n, bf16* dpre_z,
-                       bf16* dpre_h, float* dh_acc, cudaStream_t s) {
-  if (n <= 0) return SRG_OK;
-  k_gru_bwd_pre<<<grid_for(n / 4), kThreads, 0, s>>>(dh, z, hc, h, n / 4, dpre_z, dpre_h, dh_acc);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
@@ -971,13 +863,6 @@ int launch_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_i
                                                      max_norm, norm_sq, step);
   SRG_LAUNCH_CHECK();
   k_inc<<<1, 1, 0, s>>>(step);
-  SRG_LAUNCH_CHECK();
-  return SRG_OK;
-}
-
-int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t s) {
-  if (n <= 0) return SRG_OK;
-  k_fill_f32<<<grid_for(n), kThreads, 0, s>>>(p, n, v);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
