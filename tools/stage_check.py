@@ -118,6 +118,33 @@ def oracle_case(B, D, prec, train, cg=2):
             report("oracle_grad", B=B, name=k, err=relmax(got, grads[k]), ref_max=grads[k].abs().max().item())
 
 
+def bf16_agreement(B=256, D=2048):
+    """Top-1 agreement of the bf16 CUDA path with (a) the fp32 oracle and (b) the oracle run under CPU bf16 autocast
+    (what the reference's @autocast decorators would do with bf16), on random-init weights (nearly tied logits)."""
+    enc = S.imsitu_encoder(make_train_json(seed=0), verbose=False)
+    params = O.init_params(enc.get_num_verbs(), enc.get_num_roles(), enc.get_num_labels(), D, seed=0)
+    m = S.FCGGNN(enc, D, backbone=None, precision="bf16")
+    m.load_state_dict(params, strict=False)
+    m = m.cuda().eval()
+    fv, fn, gt_verb, gt_nouns = make_batch(enc, B, D, seed=1234)
+    t, c = O.build_tables(enc.roles_per_verb, enc.verb_list, enc.role_list)
+    with torch.no_grad():
+        pv32 = O.predict_verb(params, fv)
+        gpn32 = O.predict_nouns(params, fn, gt_verb, t, c)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            pv16 = O.predict_verb(params, fv).float()
+            gpn16 = O.predict_nouns(params, fn, gt_verb, t, c).float()
+        mpv = m.predict_verb(fv.cuda(), B).cpu()
+        mgpn = m.predict_nouns(fn.cuda(), gt_verb.cuda(), B).cpu()
+    ag = lambda a, b: (a.argmax(-1) == b.argmax(-1)).float().mean().item()
+    report("bf16_agreement", B=B,
+           cuda_bf16_vs_fp32_oracle={"verb": ag(mpv, pv32), "nouns": ag(mgpn, gpn32),
+                                     "err_verb": relmax(mpv, pv32), "err_nouns": relmax(mgpn, gpn32)},
+           cuda_bf16_vs_bf16_autocast_oracle={"verb": ag(mpv, pv16), "nouns": ag(mgpn, gpn16)},
+           bf16_autocast_oracle_vs_fp32_oracle={"verb": ag(pv16, pv32), "nouns": ag(gpn16, gpn32),
+                                                "err_verb": relmax(pv16, pv32), "err_nouns": relmax(gpn16, gpn32)})
+
+
 def timing(B, D=2048, cg=2, iters=5):
     enc = S.imsitu_encoder(make_train_json(seed=0), verbose=False)
     m = S.FCGGNN(enc, D, backbone=None, precision="bf16").cuda()
@@ -175,6 +202,8 @@ def main():
                 oracle_case(256, 2048, "bf16", False)
             elif st == "oracle_train":
                 oracle_case(48, 2048, "bf16", True)
+            elif st == "bf16_agreement":
+                bf16_agreement()
             elif st == "timing":
                 timing(6144)
             elif st == "timing_small":
