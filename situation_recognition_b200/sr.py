@@ -261,28 +261,35 @@ def _display(path):
         pass
 
 
+# (flag, type, default, help) -- the reference's command line (sr.py:384-420), flag for flag
+_STR_FLAGS = [("resume_model", "", "checkpoint to resume from / evaluate"),
+              ("test_img", "", "run the single-image mode on this file"),
+              ("verb", "", "ground-truth verb for --test_img"),
+              ("model_saving_name", "sr", "file name of the checkpoint"),
+              ("saving_folder", "checkpoints", "where checkpoints and the cached encoder live"),
+              ("imgset_dir", "resized_256", "directory of the images"),
+              ("dataset_folder", "imSitu", "directory of the annotation json files"),
+              ("train_file", "train.json", "training annotations"),
+              ("dev_file", "dev.json", "dev annotations"),
+              ("test_file", "test.json", "test annotations")]
+_NUM_FLAGS = [("subset", int, 0, "analyse a random dev subset of this size"),
+              ("batch_size", int, 6144, "GLOBAL batch size (split over the ranks)"),
+              ("num_workers", int, 10, "DataLoader workers"),
+              ("epochs", int, 1000, "training epochs"),
+              ("lr", float, 0.002, "Adamax learning rate")]
+
+
 def build_parser():
-    parser = ArgumentParser(description='Situation recognition with GNN.')
-    parser.add_argument('--resume_model', type=str, default='', help='The model we resume')
-    parser.add_argument('--evaluate_dev', action='store_true', help='Only use the testing mode')
-    parser.add_argument('--evaluate_test', action='store_true', help='Only use the testing mode')
-    parser.add_argument('--test_img', type=str, default='', help='Only use the results mode with a given img')
-    parser.add_argument('--verb', type=str, default='', help='Use a gt verb')
-    parser.add_argument('--subset', type=int, default=0, help='Analize a subset of a specified size')
-    parser.add_argument('--model_saving_name', type=str, default='sr', help='saving name of the outpul model')
-    parser.add_argument('--saving_folder', type=str, default='checkpoints', help='Location of annotations')
-    parser.add_argument('--imgset_dir', type=str, default='resized_256', help='Location of original images')
-    parser.add_argument('--dataset_folder', type=str, default='imSitu', help='Location of annotations')
-    parser.add_argument('--train_file', type=str, default='train.json', help='Train json file')
-    parser.add_argument('--dev_file', type=str, default='dev.json', help='Dev json file')
-    parser.add_argument('--test_file', type=str, default='test.json', help='test json file')
-    parser.add_argument('--batch_size', type=int, default=6144)
-    parser.add_argument('--num_workers', type=int, default=10)
-    parser.add_argument('--epochs', type=int, default=1000)
-    parser.add_argument('--lr', type=float, default=0.002)
+    parser = ArgumentParser(description="Situation recognition with GNN (B200-native GGNN stage).")
+    for name, default, text in _STR_FLAGS:
+        parser.add_argument("--" + name, type=str, default=default, help=text)
+    for name, kind, default, text in _NUM_FLAGS:
+        parser.add_argument("--" + name, type=kind, default=default, help=text)
+    for name in ("evaluate_dev", "evaluate_test"):
+        parser.add_argument("--" + name, action="store_true", help="only evaluate on that split")
     # extensions (not in the reference)
-    parser.add_argument('--no_pretrained', action='store_true', help='random-init backbones (no network access)')
-    parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32'])
+    parser.add_argument("--no_pretrained", action="store_true", help="random-init backbones (no network access)")
+    parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     return parser
 
 
