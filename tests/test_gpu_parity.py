@@ -341,3 +341,25 @@ def test_eager_steps_with_fused_optimizer_repack_weights(enc_syn):
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0] - 0.5          # the same batch is being fitted: stale operands would freeze the loss
+
+
+@pytest.mark.parametrize("B", [1, 13])
+def test_ragged_batches_train_step(enc_syn, B):
+    """B = 1 and an odd batch: forward + backward run, gradients are finite and match the oracle."""
+    D = 256
+    params = O.init_params(504, 190, 2001, D, seed=1)
+    fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=B)
+    t, c = O.build_tables(enc_syn.roles_per_verb, enc_syn.verb_list, enc_syn.role_list)
+    (vl, nl, gl), grads, (pv, pn, gpn) = O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, 2001)
+    m = model_from(params, enc_syn, D, "bf16").eval()
+    mpv, mpn, mgpn = m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())
+    assert mpn.shape == (B, 6, 2001)
+    lv, ln = m.verb_loss(mpv, gt_verb.cuda()), m.nouns_loss(mpn, gt_nouns.cuda())
+    (lv + ln).backward()
+    assert relmax(mgpn, gpn) <= BF16_TOL and relmax(mpv, pv) <= BF16_TOL
+    assert abs(lv.item() - float(vl)) <= 5e-3 * float(vl)
+    for k, p in m.named_parameters():
+        assert torch.isfinite(p.grad).all(), k
+    if torch.equal(mpv.argmax(-1).cpu(), pv.argmax(-1)):
+        for k, p in m.named_parameters():
+            assert relmax(p.grad, grads[k]) <= 3e-2, k

@@ -143,3 +143,38 @@ def test_bias_counted_six_times_quirk():
     agg = torch.einsum("bij,bjd->bid", mask, h.view(B, R, D)).reshape(B * R, D)
     closed = agg @ p["W_p.weight"].t() + R * p["W_p.bias"]
     assert torch.allclose(tr[0]["m"], closed, rtol=1e-5, atol=1e-5)
+
+
+def test_tables_from_any_reference_style_encoder(enc_syn):
+    """FCGGNN only needs the reference encoder API: a duck-typed object without `device_tables` yields the same
+    flat tables (this is how the reference's own imsitu_encoder instance is consumed)."""
+    from situation_recognition_b200.imsitu_encoder import tables_from_encoder
+
+    class RefStyle:
+        def __init__(self, e):
+            self.roles_to_verb_tensor_list = e.roles_to_verb_tensor_list
+            self._e = e
+
+        def get_num_verbs(self):
+            return self._e.get_num_verbs()
+
+        def get_max_role_count(self):
+            return self._e.get_max_role_count()
+
+        def get_role_count(self, v):
+            return self._e.get_role_count(v)
+
+    t0, c0 = tables_from_encoder(enc_syn)
+    t1, c1 = tables_from_encoder(RefStyle(enc_syn))
+    assert t0.dtype == np.int32 and c0.dtype == np.int32
+    assert np.array_equal(t0, t1) and np.array_equal(c0, c1)
+    assert t0.shape == (504 * 6,) and int(t0.max()) == 190 and c0.min() >= 1 and c0.max() == 6
+
+
+def test_encoder_pickles_without_transforms(enc_syn, tmp_path):
+    """sr.py caches the encoder with torch.save (sr.py:442-447)."""
+    p = tmp_path / "encoder"
+    torch.save(enc_syn, p)
+    e2 = torch.load(p, weights_only=False)
+    assert e2.verb_list == enc_syn.verb_list and torch.equal(e2.roles_to_verb_tensor_list, enc_syn.roles_to_verb_tensor_list)
+    assert e2.dev_transform is not None
