@@ -127,6 +127,16 @@ int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const f
 int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int B, const uint8_t* keep, float drop_p,
                       const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Deferred chain rule.  The verb node and the role graph share one GGNN (model.py:28-35, 226), so one training step
+ * (sr.py:63-79) calls both backward functions with the same weights.  Their gradients w.r.t. the message-side weights
+ * W_p, b_p, W_z, W_r, W_h go through the same chain rule (d/dP_x -> dW_x, dW_p, db_p; P_x = W_x W_p), which is linear
+ * in d/dP_x: with on = 1 the backward calls only accumulate d/dP_x and the bias column sums into buffers owned by the
+ * handle (safe from two streams at once), and srg_chain_finalize applies the chain rule ONCE, adds the result into `g`
+ * and clears the accumulators.  Until srg_chain_finalize has run on a stream ordered after every backward call, the
+ * five message-side gradients in `g` are incomplete.  on = 0 (default): every backward call is self-contained. */
+int srg_set_deferred_chain(srg_handle* h, int on, void* stream);
+int srg_chain_finalize(srg_handle* h, const srg_grads* g, void* stream);
+
 /* sr.py:80-83 on flat fp32 buffers of all trainable tensors (one launch instead of ~40 small ones):
  * torch.nn.utils.clip_grad_norm_(params, max_norm) -- grads are scaled in place by min(1, max_norm / (||g||_2 + 1e-6)) --
  * followed by torch.optim.Adamax(lr, betas = (beta1, beta2), eps).  scratch: device fp32 [2] = {||g||^2 of this step,

@@ -46,6 +46,8 @@ SIGNATURES = {
     "srg_nouns_backward": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _c.POINTER(SrgGrads), _vp, _sz,
                                 _vp]),
     "srg_verb_backward": (_i, [_vp, _vp, _i64, _i, _vp, _f, _c.POINTER(SrgGrads), _vp, _sz, _vp]),
+    "srg_set_deferred_chain": (_i, [_vp, _i, _vp]),
+    "srg_chain_finalize": (_i, [_vp, _c.POINTER(SrgGrads), _vp]),
     "srg_clip_adamax": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp, _vp]),
     "srg_launch_count": (_c.c_longlong, []),
     "srg_profile_begin": (_i, []),

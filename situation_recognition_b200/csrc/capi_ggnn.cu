@@ -44,6 +44,11 @@ struct srg_handle {
   float *bzr[2] = {nullptr, nullptr};       // [2D] per mode (noun, verb): b_Wx + b_Ux + c W_x b_p
   float *bh[2] = {nullptr, nullptr};        // [D]  per mode
   float *bcn = nullptr, *bcv = nullptr;
+  // ---- deferred chain rule (srg_set_deferred_chain): d/dP_x and bias column sums of ALL paths of one training step
+  bool defer_chain = false;
+  float* acc_GP = nullptr;   // [3D, D] fp32
+  bf16* acc_GPb = nullptr;   // [3D, D] bf16 operand copy
+  float* acc_s = nullptr;    // [3D]
 };
 
 namespace {
@@ -336,6 +341,46 @@ int classifier_forward(srg_handle* h, int mode, PathBufs& pb, const float* h32, 
   return run_gemm(p, h->dev, s);
 }
 
+// ------------------------------------------------------------------------------------------------ chain rule
+// Through P_x = W_x W_p and b'_x = b_Wx + b_Ux + c W_x b_p  (x = h, z, r):
+//   dW_x += dP_x W_p^T + s_x (x) b_p,   dW_p += sum_x W_x^T dP_x,   db_p += sum_x W_x^T s_x,   s_x = c colsum(dpre_x).
+// shared_dst: another stream may be accumulating into the same gradients (per-path mode on two streams).
+int chain_rule(srg_handle* h, const float* G_P, bf16* G_Pb, const float* s_all, const srg_grads* g, bool shared_dst,
+               cudaStream_t s) {
+  const int D = h->D;
+  SRG_TRY(launch_split_cast(G_P, static_cast<int64_t>(3) * D * D, G_Pb, nullptr, nullptr, s));
+  float* gW[3] = {g->W_h, g->W_z, g->W_r};
+  const float* W32[3] = {h->params.W_h, h->params.W_z, h->params.W_r};
+  for (int x3 = 0; x3 < 3; ++x3) {
+    if (gW[x3] == nullptr) continue;
+    GemmProblem p = base_problem(h, D, D);
+    add_seg(p, G_Pb + static_cast<size_t>(x3) * D * D, D, D, 0, D);
+    p.b = mat(h->Wp6, D, D, D, DT_BF16);  // first block of Wp6 = bf16(W_p), K-major [k, i]
+    p.epi = EPI_STORE_F32;
+    p.flags = FLAG_REDUCE;
+    p.io[0] = mat(gW[x3], D, D, D, DT_F32);
+    SRG_TRY(run_gemm(p, h->dev, s));
+  }
+  SRG_TRY(launch_outer_acc3(s_all, h->params.b_p, D, D, gW, shared_dst, s));
+  if (g->b_p != nullptr) SRG_TRY(launch_matvec_t_acc3(W32, s_all, D, D, g->b_p, s));
+  if (g->W_p != nullptr) {  // dW_p += [W_h; W_z; W_r]^T [dP_h; dP_z; dP_r]
+    GemmProblem p = base_problem(h, D, D);
+    p.a_mn = true;
+    p.b_mn = true;
+    p.nseg = 1;
+    p.seg[0].a = mat(h->Wm_hi, 3 * D, D, D, DT_BF16);
+    p.seg[0].k_off = 0;
+    p.seg[0].k_len = 3 * D;
+    p.b = mat(G_Pb, 3 * D, D, D, DT_BF16);
+    p.epi = EPI_STORE_F32;
+    p.flags = FLAG_REDUCE;
+    p.io[0] = mat(g->W_p, D, D, D, DT_F32);
+    p.k_splits = wgrad_splits(h, D, D, 3 * D);
+    SRG_TRY(run_gemm(p, h->dev, s));
+  }
+  return SRG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, int64_t ldl, int B,
                   const uint8_t* keep, float drop_p, const srg_grads* g, cudaStream_t s) {
@@ -351,8 +396,14 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
   const bool use_drop = (keep != nullptr && drop_p > 0.f);
   const bf16* x = use_drop ? pb.xd_hi : pb.hb_hi[T];
 
-  SRG_CUDA(cudaMemsetAsync(pb.G_P, 0, sizeof(float) * 3 * D * D, s));
-  SRG_CUDA(cudaMemsetAsync(pb.s_all, 0, sizeof(float) * 3 * D, s));
+  // d/dP_x and the bias column sums: per call, or (deferred chain rule) shared by all paths of the step
+  const bool defer = h->defer_chain;
+  float* G_P = defer ? h->acc_GP : pb.G_P;
+  float* s_all = defer ? h->acc_s : pb.s_all;
+  if (!defer) {
+    SRG_CUDA(cudaMemsetAsync(G_P, 0, sizeof(float) * 3 * D * D, s));
+    SRG_CUDA(cudaMemsetAsync(s_all, 0, sizeof(float) * 3 * D, s));
+  }
 
   // ---- classifier (model.py:105-111,152,168)
   SRG_TRY(launch_cast_pad(dlogits, ldl, M, ncls, npad, pb.dlb, s));
@@ -432,50 +483,19 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
     const int KM = T * M;
     bf16* dp = pb.dpre_all;
     const bf16* a_all = (mode == SRG_MODE_NOUN) ? pb.st[0].a_hi : pb.hb_hi[0];   // contiguous over t = 0..T-1
-    SRG_TRY(wgrad(h, dp, ld3, 3 * D, a_all, D, KM, pb.G_P, s));              // dP_h, dP_z, dP_r in one GEMM
+    SRG_TRY(wgrad(h, dp, ld3, 3 * D, a_all, D, KM, G_P, s));                 // dP_h, dP_z, dP_r in one GEMM
     SRG_TRY(wgrad(h, dp + D, ld3, D, pb.hb_hi[0], D, KM, g->U_z, s));
     SRG_TRY(wgrad(h, dp + 2 * D, ld3, D, pb.hb_hi[0], D, KM, g->U_r, s));
     SRG_TRY(wgrad(h, dp, ld3, D, pb.st[0].rh_hi, D, KM, g->U_h, s));
-    ColsumJob jobs[3] = {{dp, g->b_Wh, g->b_Uh, 1.f, pb.s_all, cmul},
-                         {dp + D, g->b_Wz, g->b_Uz, 1.f, pb.s_all + D, cmul},
-                         {dp + 2 * D, g->b_Wr, g->b_Ur, 1.f, pb.s_all + 2 * D, cmul}};
+    ColsumJob jobs[3] = {{dp, g->b_Wh, g->b_Uh, 1.f, s_all, cmul},
+                         {dp + D, g->b_Wz, g->b_Uz, 1.f, s_all + D, cmul},
+                         {dp + 2 * D, g->b_Wr, g->b_Ur, 1.f, s_all + 2 * D, cmul}};
     SRG_TRY(launch_colsum_multi(jobs, 3, ld3, KM, D, s));
   }
   pb.dh = dh_acc;  // gradient w.r.t. the initial node states
 
-  // ---- chain rule through P_x = W_x W_p and b'_x = b_Wx + b_Ux + c W_x b_p   (x = h, z, r)
-  SRG_TRY(launch_split_cast(pb.G_P, static_cast<int64_t>(3) * D * D, pb.G_Pb, nullptr, nullptr, s));
-  float* gW[3] = {g->W_h, g->W_z, g->W_r};
-  const float* W32[3] = {h->params.W_h, h->params.W_z, h->params.W_r};
-  for (int x3 = 0; x3 < 3; ++x3) {
-    if (gW[x3] != nullptr) {  // dW_x += dP_x W_p^T  + s_x (x) b_p
-      GemmProblem p = base_problem(h, D, D);
-      add_seg(p, pb.G_Pb + static_cast<size_t>(x3) * D * D, D, D, 0, D);
-      p.b = mat(h->Wp6, D, D, D, DT_BF16);  // first block of Wp6 = bf16(W_p), K-major [k, i]
-      p.epi = EPI_STORE_F32;
-      p.flags = FLAG_REDUCE;
-      p.io[0] = mat(gW[x3], D, D, D, DT_F32);
-      SRG_TRY(run_gemm(p, h->dev, s));
-      SRG_TRY(launch_outer_acc(pb.s_all + x3 * D, h->params.b_p, D, D, gW[x3], s));
-    }
-    if (g->b_p != nullptr) SRG_TRY(launch_matvec_t_acc(W32[x3], pb.s_all + x3 * D, D, D, g->b_p, s));
-  }
-  if (g->W_p != nullptr) {  // dW_p += [W_h; W_z; W_r]^T [dP_h; dP_z; dP_r]
-    GemmProblem p = base_problem(h, D, D);
-    p.a_mn = true;
-    p.b_mn = true;
-    p.nseg = 1;
-    p.seg[0].a = mat(h->Wm_hi, 3 * D, D, D, DT_BF16);
-    p.seg[0].k_off = 0;
-    p.seg[0].k_len = 3 * D;
-    p.b = mat(pb.G_Pb, 3 * D, D, D, DT_BF16);
-    p.epi = EPI_STORE_F32;
-    p.flags = FLAG_REDUCE;
-    p.io[0] = mat(g->W_p, D, D, D, DT_F32);
-    p.k_splits = wgrad_splits(h, D, D, 3 * D);
-    SRG_TRY(run_gemm(p, h->dev, s));
-  }
-  return SRG_OK;
+  if (defer) return SRG_OK;   // srg_chain_finalize applies the chain rule once for all paths
+  return chain_rule(h, G_P, pb.G_Pb, s_all, g, /*shared_dst=*/true, s);
 }
 
 int ensure_pack_buffers(srg_handle* h, int split) {
@@ -560,7 +580,8 @@ int srg_create(srg_handle** out, int device, int D, int R, int T, int n_verbs, i
 int srg_destroy(srg_handle* h) {
   if (!h) return SRG_OK;
   void* ptrs[] = {h->d_verb2roles, h->d_role_count, h->d_bad, h->Wzr, h->Wh, h->Wcn, h->Wcv, h->Wm_hi, h->Wm_mid, h->Wm_lo, h->Wp6,
-                  h->P_hi, h->P_mid, h->P_lo, h->U_stack, h->Uh, h->wb, h->bzr[0], h->bzr[1], h->bh[0], h->bh[1], h->bcn, h->bcv};
+                  h->P_hi, h->P_mid, h->P_lo, h->U_stack, h->Uh, h->wb, h->bzr[0], h->bzr[1], h->bh[0], h->bh[1], h->bcn, h->bcv,
+                  h->acc_GP, h->acc_GPb, h->acc_s};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete h;
@@ -774,6 +795,35 @@ int srg_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf,
   SRG_CHECK(params && grads && exp_avg && exp_inf && scratch, "srg_clip_adamax: null argument");
   return launch_clip_adamax(params, grads, exp_avg, exp_inf, n, lr, beta1, beta2, eps, max_norm, scratch, scratch + 1,
                             static_cast<cudaStream_t>(stream));
+}
+
+int srg_set_deferred_chain(srg_handle* h, int on, void* stream) {
+  SRG_CHECK(h != nullptr, "null handle");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t D = h->D;
+  if (on && h->acc_GP == nullptr) {
+    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->acc_GP), 3 * D * D * sizeof(float)));
+    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->acc_GPb), 3 * D * D * sizeof(bf16)));
+    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->acc_s), 3 * D * sizeof(float)));
+  }
+  if (on) {
+    SRG_CUDA(cudaMemsetAsync(h->acc_GP, 0, 3 * D * D * sizeof(float), s));
+    SRG_CUDA(cudaMemsetAsync(h->acc_s, 0, 3 * D * sizeof(float), s));
+  }
+  h->defer_chain = (on != 0);
+  return SRG_OK;
+}
+
+int srg_chain_finalize(srg_handle* h, const srg_grads* g, void* stream) {
+  SRG_CHECK(h != nullptr && g != nullptr, "srg_chain_finalize: null argument");
+  SRG_CHECK(h->defer_chain && h->acc_GP != nullptr, "srg_chain_finalize: call srg_set_deferred_chain(h, 1) first");
+  SRG_CHECK(h->packed_prec == SRG_PREC_BF16, "srg_chain_finalize needs bf16-packed weights");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t D = h->D;
+  SRG_TRY(chain_rule(h, h->acc_GP, h->acc_GPb, h->acc_s, g, /*shared_dst=*/false, s));
+  SRG_CUDA(cudaMemsetAsync(h->acc_GP, 0, 3 * D * D * sizeof(float), s));
+  SRG_CUDA(cudaMemsetAsync(h->acc_s, 0, 3 * D * sizeof(float), s));
+  return SRG_OK;
 }
 
 int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const float* feat, const int64_t* verb, int B,

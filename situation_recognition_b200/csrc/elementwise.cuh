@@ -89,10 +89,12 @@ int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const 
                           bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc, cudaStream_t s);
 // y[o] = sum_k W[o,k] x[k]                       (fp32, W row-major [rows, cols])
 int launch_matvec(const float* W, const float* x, int rows, int cols, float* y, cudaStream_t s);
-// y[k] += sum_o W[o,k] s[o]
-int launch_matvec_t_acc(const float* W, const float* sv, int rows, int cols, float* y, cudaStream_t s);
-// dW[o,k] += s[o] * b[k]
-int launch_outer_acc(const float* sv, const float* b, int rows, int cols, float* dW, cudaStream_t s);
+// y[k] += sum_x sum_o W_x[o,k] s[x*rows + o]    (three [rows, cols] matrices in one launch; null W_x skipped)
+int launch_matvec_t_acc3(const float* const W[3], const float* sv, int rows, int cols, float* y, cudaStream_t s);
+// dW_x[o,k] += s[x*rows + o] * b[k]              (three matrices in one launch; null dW_x skipped);
+// atomic = the destination may be accumulated into from another stream at the same time
+int launch_outer_acc3(const float* sv, const float* b, int rows, int cols, float* const dW[3], bool atomic,
+                      cudaStream_t s);
 // dst[i] = a[i] + b[i] + scale * c[i]   (b, c nullable; zero beyond n up to n_pad)
 int launch_pack_bias3(const float* a, const float* b, const float* c, float scale, int n, int n_pad, float* dst,
                       cudaStream_t s);

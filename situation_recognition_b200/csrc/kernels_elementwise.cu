@@ -555,25 +555,54 @@ __global__ void k_matvec(const float* __restrict__ W, const float* __restrict__ 
   if (lane == 0) y[row] = acc;
 }
 
-// grid = (cols / 256, row slabs); y[k] += sum over the slab of W[o,k] s[o]
-__global__ void k_matvec_t_acc(const float* __restrict__ W, const float* __restrict__ sv, int rows, int cols,
-                               float* __restrict__ y) {
+struct Mat3 {
+  const float* W[3];
+  float* dW[3];
+};
+// grid = (cols / 256, row slabs, 3 matrices); y[k] += sum over the slab of W_x[o,k] s[x*rows + o]
+__global__ void k_matvec_t_acc3(Mat3 m, const float* __restrict__ sv, int rows, int cols, float* __restrict__ y) {
+  const float* __restrict__ W = m.W[blockIdx.z];
+  const float* __restrict__ s = sv + static_cast<int64_t>(blockIdx.z) * rows;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
-  if (k >= cols) return;
-  float acc = 0.f;
-  for (int o = r0; o < r1; ++o) acc = fmaf(W[static_cast<int64_t>(o) * cols + k], sv[o], acc);
-  atomicAdd(y + k, acc);
+  if (k >= cols || W == nullptr) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent loads in flight
+  int o = r0;
+  for (; o + 3 < r1; o += 4) {
+    const float* w = W + static_cast<int64_t>(o) * cols + k;
+    a0 = fmaf(w[0], s[o], a0);
+    a1 = fmaf(w[cols], s[o + 1], a1);
+    a2 = fmaf(w[2 * static_cast<int64_t>(cols)], s[o + 2], a2);
+    a3 = fmaf(w[3 * static_cast<int64_t>(cols)], s[o + 3], a3);
+  }
+  for (; o < r1; ++o) a0 = fmaf(W[static_cast<int64_t>(o) * cols + k], s[o], a0);
+  atomicAdd(y + k, (a0 + a1) + (a2 + a3));
 }
 
-__global__ void k_outer_acc(const float* __restrict__ sv, const float* __restrict__ b, int rows, int cols,
-                            float* __restrict__ dW) {
-  const int64_t total = static_cast<int64_t>(rows) * cols;
+// grid = (chunks, 3 matrices); dW_x[o,k] += s[x*rows + o] * b[k], four columns per thread.
+// ATOMIC: the verb and noun backward passes may accumulate into the same dW from two streams.
+template <bool ATOMIC>
+__global__ void k_outer_acc3(Mat3 m, const float* __restrict__ sv, const float* __restrict__ b, int rows, int cols) {
+  float* __restrict__ dW = m.dW[blockIdx.y];
+  if (dW == nullptr) return;
+  const float* __restrict__ s = sv + static_cast<int64_t>(blockIdx.y) * rows;
+  const int c4 = cols >> 2;
+  const int64_t total = static_cast<int64_t>(rows) * c4;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int o = static_cast<int>(t / cols), k = static_cast<int>(t % cols);
-    atomicAdd(dW + t, sv[o] * b[k]);   // the verb and noun backward passes may run concurrently on two streams
+    const int o = static_cast<int>(t / c4), k = static_cast<int>(t % c4) * 4;
+    const float so = s[o];
+    const float4 bv = *reinterpret_cast<const float4*>(b + k);
+    float4* dst = reinterpret_cast<float4*>(dW + static_cast<int64_t>(o) * cols + k);
+    const float4 upd = make_float4(so * bv.x, so * bv.y, so * bv.z, so * bv.w);
+    if constexpr (ATOMIC) {
+      atomicAdd(dst, upd);
+    } else {
+      float4 v = *dst;
+      v.x += upd.x; v.y += upd.y; v.z += upd.z; v.w += upd.w;
+      *dst = v;
+    }
   }
 }
 
@@ -832,15 +861,25 @@ int launch_matvec(const float* W, const float* x, int rows, int cols, float* y, 
   return SRG_OK;
 }
 
-int launch_matvec_t_acc(const float* W, const float* sv, int rows, int cols, float* y, cudaStream_t s) {
-  dim3 grid((cols + kThreads - 1) / kThreads, 32);
-  k_matvec_t_acc<<<grid, kThreads, 0, s>>>(W, sv, rows, cols, y);
+int launch_matvec_t_acc3(const float* const W[3], const float* sv, int rows, int cols, float* y, cudaStream_t s) {
+  Mat3 m;
+  for (int i = 0; i < 3; ++i) { m.W[i] = W[i]; m.dW[i] = nullptr; }
+  int slabs = (rows + 31) / 32;
+  if (slabs > 128) slabs = 128;
+  dim3 grid((cols + kThreads - 1) / kThreads, slabs, 3);
+  k_matvec_t_acc3<<<grid, kThreads, 0, s>>>(m, sv, rows, cols, y);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
-int launch_outer_acc(const float* sv, const float* b, int rows, int cols, float* dW, cudaStream_t s) {
-  k_outer_acc<<<grid_for(static_cast<int64_t>(rows) * cols), kThreads, 0, s>>>(sv, b, rows, cols, dW);
+int launch_outer_acc3(const float* sv, const float* b, int rows, int cols, float* const dW[3], bool atomic,
+                      cudaStream_t s) {
+  if (cols % 4 != 0) return set_error(SRG_ERR_ARG, "outer_acc3: cols=%d must be a multiple of 4", cols);
+  Mat3 m;
+  for (int i = 0; i < 3; ++i) { m.W[i] = nullptr; m.dW[i] = dW[i]; }
+  dim3 grid(grid_for(static_cast<int64_t>(rows) * cols / 4, kThreads, 148 * 8), 3);
+  if (atomic) k_outer_acc3<true><<<grid, kThreads, 0, s>>>(m, sv, b, rows, cols);
+  else k_outer_acc3<false><<<grid, kThreads, 0, s>>>(m, sv, b, rows, cols);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }

@@ -80,6 +80,9 @@ class _Engine:
                                            rc.ctypes.data_as(ctypes.c_void_p)))
         self._packed_key = None
         self.launches = 0
+        self._deferred = False     # srg_set_deferred_chain state of the handle
+        self._pending = None       # direct-gradient backward pass in flight: {"grads", "events"}
+        self._events = []
 
     def __del__(self):
         try:
@@ -112,6 +115,48 @@ class _Engine:
         sp = _lib.SrgParams(*[ctypes.c_void_p(p.data_ptr()) for p in params])
         _lib.check(self.lib.srg_pack_weights(self.h, ctypes.byref(sp), prec, _lib.stream_ptr()))
         self._packed_key = key
+
+    # ---- direct-gradient backward passes (flat buffers): one chain rule for all paths, one join of the side streams
+    def set_deferred(self, on):
+        if on == self._deferred:
+            return
+        if self._pending is not None:
+            self.finish_backward()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srg_set_deferred_chain(self.h, int(on), _lib.stream_ptr()))
+            if on:
+                torch.cuda.current_stream().synchronize()   # one-off: the cleared accumulators are visible to all streams
+        self._deferred = on
+
+    def backward_begin(self, grads):
+        """First direct-mode backward call of an autograd pass: defer the chain rule through the folded message weights
+        and have the autograd engine call finish_backward() when the whole pass has been queued."""
+        self.set_deferred(True)
+        if self._pending is None:
+            self._pending = {"grads": grads, "events": []}
+            torch.autograd.Variable._execution_engine.queue_callback(self.finish_backward)
+
+    def backward_mark(self):
+        """Record the end of one path's backward kernels on the stream they were queued on."""
+        k = len(self._pending["events"])
+        if k >= len(self._events):
+            self._events.append(torch.cuda.Event())
+        ev = self._events[k]
+        ev.record(torch.cuda.current_stream(self.device))
+        self._pending["events"].append(ev)
+
+    def finish_backward(self):
+        """Runs on the stream that called backward(): wait for every path (they may have run on side streams -- autograd
+        does not join streams of functions that return no gradients), then apply the chain rule once."""
+        pend, self._pending = self._pending, None
+        if pend is None:
+            return
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream()
+            for ev in pend["events"]:
+                cur.wait_event(ev)
+            sg = _grad_struct(pend["grads"], self)
+            _lib.check(self.lib.srg_chain_finalize(self.h, ctypes.byref(sg), _lib.stream_ptr()))
 
     def workspace(self, mode, B, prec, save):
         n = self.lib.srg_workspace_bytes(self.h, mode, B, prec, int(save))
@@ -189,14 +234,17 @@ class _NounsStage(torch.autograd.Function):
         names = ["role_emb", "verb_emb"] + _GGNN_FIELDS + ["Wc_noun", "bc_noun"]
         if ctx.direct:   # flat-buffer mode: the kernels accumulate straight into the (pre-zeroed) .grad views
             grads = {n: p.grad for n, p in zip(names, ctx.live)}
+            eng.backward_begin(grads)
         else:
             grads = {n: torch.zeros_like(p) for n, p in zip(names, (role_emb, verb_emb) + tuple(params))}
+            eng.set_deferred(False)
         sg = _grad_struct(grads, eng)
         _lib.check(eng.lib.srg_nouns_backward(eng.h, _lib.ptr(dl), ldl, _lib.ptr(feat), _lib.ptr(verb), B,
                                               _lib.ptr(role_emb), _lib.ptr(verb_emb), _lib.ptr(keep), ctx.drop_p,
                                               ctypes.byref(sg), _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()))
         ctx.ws = None
         if ctx.direct:
+            eng.backward_mark()
             return (None,) * (5 + len(names))
         out = [grads[n] for n in _GGNN_FIELDS + ["Wc_noun", "bc_noun"]]
         return (None, None, None, None, None, grads["role_emb"], grads["verb_emb"], *out)
@@ -237,13 +285,16 @@ class _VerbStage(torch.autograd.Function):
         names = _GGNN_FIELDS + ["Wc_verb", "bc_verb"]
         if ctx.direct:
             grads = {n: p.grad for n, p in zip(names, ctx.live)}
+            eng.backward_begin(grads)
         else:
             grads = {n: torch.zeros_like(p) for n, p in zip(names, params)}
+            eng.set_deferred(False)
         sg = _grad_struct(grads, eng)
         _lib.check(eng.lib.srg_verb_backward(eng.h, _lib.ptr(dl), ldl, B, _lib.ptr(keep), ctx.drop_p, ctypes.byref(sg),
                                              _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()))
         ctx.ws = None
         if ctx.direct:
+            eng.backward_mark()
             return (None,) * (4 + len(names))
         return (None, None, None, None, *[grads[n] for n in names])
 

@@ -17,19 +17,30 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+_ALIGN = 64   # elements: every tensor starts on a 256-byte boundary of the flat buffer (TMA needs 16 bytes)
+
+
+def flat_layout(params, align=_ALIGN):
+    """(offsets, padded total) of `params` laid out back to back with each start rounded up to `align` elements."""
+    offsets, off = [], 0
+    for p in params:
+        offsets.append(off)
+        off += (p.numel() + align - 1) // align * align
+    return offsets, off
+
+
 class FlatGrads:
     """All trainable gradients live in ONE flat fp32 buffer (per-parameter `.grad` tensors are views of it), so a
-    step needs a single all-reduce launch and clip/optimizer see ordinary `.grad` tensors."""
+    step needs a single all-reduce launch and clip/optimizer see ordinary `.grad` tensors.  The gaps that align the
+    tensors stay zero."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        self.offsets, n = flat_layout(self.params)
         ref = self.params[0]
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
 
     def zero(self):
         self.flat.zero_()
@@ -64,24 +75,19 @@ class FlatParams(FlatGrads):
 
     def __init__(self, params):
         params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in params)
-        n_pad = (n + 3) // 4 * 4
+        self.offsets, n_pad = flat_layout(params)
         ref = params[0]
         self.flat_param = torch.zeros(n_pad, dtype=ref.dtype, device=ref.device)
-        off = 0
         with torch.no_grad():
-            for p in params:
+            for p, off in zip(params, self.offsets):
                 view = self.flat_param[off:off + p.numel()].view_as(p)
                 view.copy_(p.data)
                 p.data = view
-                off += p.numel()
         self.params = params
         self.version = 0   # bumped by FlatAdamax.step(): raw kernels do not touch torch's tensor version counters
         self.flat = torch.zeros(n_pad, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in params:
+        for p, off in zip(params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
 
 
 class FlatAdamax(torch.optim.Optimizer):
@@ -100,12 +106,10 @@ class FlatAdamax(torch.optim.Optimizer):
         self.exp_avg = torch.zeros_like(flat.flat)
         self.exp_inf = torch.zeros_like(flat.flat)
         self.scratch = torch.zeros(2, dtype=torch.float32, device=dev)   # {||g||^2, steps taken}
-        off = 0
-        for p in flat.params:
+        for p, off in zip(flat.params, flat.offsets):
             n = p.numel()
             self.state[p] = {"step": self.scratch[1], "exp_avg": self.exp_avg[off:off + n].view_as(p),
                              "exp_inf": self.exp_inf[off:off + n].view_as(p)}
-            off += n
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -120,10 +120,17 @@ def test_golden_forward(enc_over, precision, tol, cta_group):
         assert abs(m.nouns_loss(gpn, gt_nouns).item() - float(g["gt_nouns_loss"])) <= ltol * float(g["gt_nouns_loss"])
 
 
-def test_golden_gradients(enc_over):
-    """autograd of the unmodified reference (verb_loss + nouns_loss, sr.py:76) vs the CUDA backward (bf16 operands)."""
+@pytest.mark.parametrize("flat", [False, True])
+def test_golden_gradients(enc_over, flat):
+    """autograd of the unmodified reference (verb_loss + nouns_loss, sr.py:76) vs the CUDA backward (bf16 operands).
+    flat: gradients accumulated straight into one flat buffer (odd vocabulary sizes: every view must stay aligned) with
+    the chain rule through the folded message weights applied once for both paths."""
     g = golden("model_overfitting_D256.npz")
     m = model_from(golden_params(g), enc_over, 256, "bf16").eval()
+    if flat:
+        from situation_recognition_b200 import parallel
+        fb = parallel.attach(m, flat_params=True)
+        assert all(p.grad.data_ptr() % 256 == 0 and p.data_ptr() % 256 == 0 for p in fb.params)
     feat, gt_verb = torch.from_numpy(g["feat"]).cuda(), torch.from_numpy(g["gt_verb"]).cuda()
     gt_nouns = torch.from_numpy(g["gt_nouns"]).cuda()
     pv, pn, gpn = m(feat, gt_verb)
@@ -210,7 +217,8 @@ def test_images_are_independent_and_batch_one(enc_syn, cfg2):
     assert torch.equal(one[0], full[3]) and torch.equal(seven, full[100:107]) and torch.equal(vone[0], vfull[9])
 
 
-def test_train_step_gradients_vs_oracle(enc_syn):
+@pytest.mark.parametrize("flat", [False, True])
+def test_train_step_gradients_vs_oracle(enc_syn, flat):
     B, D = 48, 2048
     params = O.init_params(504, 190, 2001, D, seed=0)
     fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=77)
@@ -221,9 +229,19 @@ def test_train_step_gradients_vs_oracle(enc_syn):
     (vl, nl, gl), grads, (pv, pn, gpn) = O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, 2001, keeps, 0.5)
     m = model_from(params, enc_syn, D, "bf16").train()
     m.dropout_masks = tuple(k.to(torch.uint8).cuda() for k in keeps)
+    if flat:     # direct accumulation into the flat buffer, deferred chain rule, side-stream join at the end of backward
+        from situation_recognition_b200 import parallel
+        parallel.attach(m)
     mpv, mpn, mgpn = m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())
     lv, ln, lg = m.verb_loss(mpv, gt_verb.cuda()), m.nouns_loss(mpn, gt_nouns.cuda()), m.nouns_loss(mgpn, gt_nouns.cuda())
     (lv + ln).backward()
+    if flat:     # a second pass accumulates: twice the gradient (the handle-level accumulators were cleared in between)
+        first = {k: p.grad.clone() for k, p in m.named_parameters()}
+        mpv2, mpn2, _ = m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())
+        (m.verb_loss(mpv2, gt_verb.cuda()) + m.nouns_loss(mpn2, gt_nouns.cuda())).backward()
+        for k, p in m.named_parameters():
+            assert relmax(p.grad, 2 * first[k]) <= 1e-3, k
+            p.grad.copy_(first[k])
     assert relmax(mgpn, gpn) <= BF16_TOL and relmax(mpv, pv) <= BF16_TOL       # dropout-mask parity included
     assert abs(lv.item() - float(vl)) <= 2e-3 * float(vl) and abs(lg.item() - float(gl)) <= 2e-3 * float(gl)
     if torch.equal(mpv.argmax(-1).cpu(), pv.argmax(-1)):       # same predicted verbs => same pred-noun graph
