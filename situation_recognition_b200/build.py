@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
     "-diag-suppress", "550",
-]
+] + os.environ.get("SRG_NVCC_EXTRA", "").split()      # e.g. -DSRG_EPI_TIMING (tools/epi_timing.py)
 
 
 def _digest():

@@ -852,4 +852,15 @@ int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int B, c
   return path_backward(h, SRG_MODE_VERB, pb, dlogits, ldl, B, keep, drop_p, g, static_cast<cudaStream_t>(stream));
 }
 
+#ifdef SRG_EPI_TIMING
+/* debug builds only (tools/epi_timing.py): copy out and optionally clear the epilogue clock counters [8 kinds][8] */
+int srg_debug_epi_timing(unsigned long long* out, int reset) {
+  SRG_CUDA(cudaDeviceSynchronize());
+  SRG_CHECK(srg::g_epi_t_dev != nullptr, "no GEMM has been launched yet");
+  SRG_CUDA(cudaMemcpy(out, srg::g_epi_t_dev, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost));
+  if (reset) SRG_CUDA(cudaMemset(srg::g_epi_t_dev, 0, sizeof(unsigned long long) * 64));
+  return SRG_OK;
+}
+#endif
+
 }  // extern "C"

@@ -63,6 +63,9 @@ struct GemmArgs {
   int n_valid;   // EPI_LOGITS: number of real columns (the rest is padding)
   float* stats;  // EPI_LOGITS: [M][N / BLOCK_N][2] (row max, row sum-exp) per column tile
   int flags;
+#ifdef SRG_EPI_TIMING
+  unsigned long long* epi_t;  // debug build: [8 kinds][8] clock counters (see tools/epi_timing.py)
+#endif
 };
 
 template <int EPI, bool F32>
@@ -188,6 +191,17 @@ __device__ __forceinline__ void load_bias8(const float* bias, int col, float sca
   b[0] = x.x * scale; b[1] = x.y * scale; b[2] = x.z * scale; b[3] = x.w * scale;
   b[4] = y.x * scale; b[5] = y.y * scale; b[6] = y.z * scale; b[7] = y.w * scale;
 }
+
+// Debug build (-DSRG_EPI_TIMING, tools/epi_timing.py): SM-clock breakdown of the pipelined epilogues, summed over all
+// epilogue warps per EPI kind: {tiles, chunks, tile total, wait accumulator, wait inputs, wait stores + issue,
+// tmem ld + math, store issue}.
+#ifdef SRG_EPI_TIMING
+#define SRG_T(var) const long long var = clock64()
+#define SRG_TACC(i, a, b) tacc_[i] += static_cast<unsigned long long>((b) - (a))
+#else
+#define SRG_T(var)
+#define SRG_TACC(i, a, b)
+#endif
 
 }  // namespace srg
 #include "epilogue_pipe.cuh"
@@ -400,6 +414,9 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
       int set = 0;
       uint32_t ph = 0;
       bool issued = false;   // the loads of the chunk about to be processed are already in flight
+#ifdef SRG_EPI_TIMING
+      unsigned long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
       for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
         const int row0 = row_of(w), n0 = n0_of(w);
         const int acc = iter & 1;
@@ -408,6 +425,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
         const bool tin = needs_in(n0);
         const bool r_tile = (EPI == EPI_ZR) && tin;
         const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+        SRG_T(tile_t0);
         if (!active) {
           ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
         } else {
@@ -423,18 +441,22 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
               nvalid = (nw < total_work) && (row_of(nw) < args.M);
             }
             const bool pre = nvalid && needs_in(n0_of(nw));
+            SRG_T(c0);
             if (lane == 0 && tin && !issued) {   // only the first chunk of a run is not prefetched
               ptx::tma_wait_group_read<0>();
               pipe_issue<EPI>(ctx, sp, &bar2[set], n0, cc, row0);
             }
+            SRG_T(c1);
             if (cc == 0) {
               ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
               ptx::tcgen05_fence_after();
             }
+            SRG_T(c2);
             if (tin) {
               ptx::mbar_wait(&bar2[set], (ph >> set) & 1u);
               ph ^= (1u << set);
             }
+            SRG_T(c3);
             if (lane == 0) {
               if (pre) {     // the other set's last stores were committed one iteration ago
                 ptx::tma_wait_group_read<0>();
@@ -445,23 +467,40 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
             }
             issued = pre;
             if (!tin) __syncwarp();              // output-only chunk: lanes must not overwrite the set before that wait
+            SRG_T(c4);
             float accv[32];
             ptx::tmem_ld_32x32(tacc + cc * 32, accv);
             ptx::tmem_ld_wait();
             pipe_compute<EPI>(ctx, ptx::smem_u32(sp), accv, n0, cc, r_tile);
             ptx::fence_proxy_async_smem();
             __syncwarp();
+            SRG_T(c5);
             if (lane == 0) {
               pipe_store<EPI>(ctx, sp, n0, cc, row0, r_tile);
               ptx::tma_commit_group();
             }
+            SRG_T(c6);
+            SRG_TACC(1, 0, 1);
+            SRG_TACC(3, c1, c2);
+            SRG_TACC(4, c2, c3);
+            SRG_TACC(5, c0, c1);
+            SRG_TACC(5, c3, c4);
+            SRG_TACC(6, c4, c5);
+            SRG_TACC(7, c5, c6);
             set ^= 1;
           }
         }
         ptx::tcgen05_fence_before();
         if constexpr (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
         else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        SRG_T(tile_t1);
+        SRG_TACC(0, 0, 1);
+        SRG_TACC(2, tile_t0, tile_t1);
       }
+#ifdef SRG_EPI_TIMING
+      if (lane == 0 && args.epi_t != nullptr)
+        for (int i = 0; i < 8; ++i) atomicAdd(&args.epi_t[EPI * 8 + i], tacc_[i]);
+#endif
       if (lane == 0) ptx::tma_wait_group<0>();
       __syncwarp();
     } else

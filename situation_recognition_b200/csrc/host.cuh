@@ -66,6 +66,9 @@ struct ProfState {
   double flops[kProfMaxRecords];
 };
 inline ProfState g_prof;
+#ifdef SRG_EPI_TIMING
+inline unsigned long long* g_epi_t_dev = nullptr;   // one instance per process (inline variable), allocated on first use
+#endif
 inline int prof_kind(int epi, bool a_mn, bool b_mn) { return epi * 4 + (a_mn ? 2 : 0) + (b_mn ? 1 : 0); }
 
 // ---------------------------------------------------------------- TMA descriptors
@@ -330,6 +333,13 @@ inline int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t st
   args.n_valid = p.n_valid;
   args.stats = p.stats;
   args.flags = p.flags;
+#ifdef SRG_EPI_TIMING
+  if (g_epi_t_dev == nullptr) {
+    SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_epi_t_dev), 64 * sizeof(unsigned long long)));
+    SRG_CUDA(cudaMemset(g_epi_t_dev, 0, 64 * sizeof(unsigned long long)));
+  }
+  args.epi_t = g_epi_t_dev;
+#endif
 
   if (p.cg == 2) return dispatch_gemm<2, 256>(p, maps, args, dev, stream);
   return dispatch_gemm<1, 128>(p, maps, args, dev, stream);
