@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrggnn.so")
+# SRG_LIB_PATH: load another build of the library (A/B measurements of two revisions on the same GPU box)
+LIB_PATH = os.environ.get("SRG_LIB_PATH") or os.path.join(_HERE, "libsrggnn.so")
 
 SRG_DT_F32, SRG_DT_BF16 = 1, 2
 SRG_PREC_BF16, SRG_PREC_FP32 = 0, 1

@@ -12,8 +12,9 @@
 // * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA), warp 2 = TMEM allocator,
 //   warps 4..7 = epilogue (one TMEM lane quarter each). Accumulators are double-buffered in TMEM so the
 //   epilogue of tile i overlaps the main loop of tile i+1.
-// * Epilogue I/O goes through TMA: every elementwise operand/result is moved as [32 rows x 128 B]
-//   SWIZZLE_128B boxes, per warp, so no global LSU traffic and no uncoalesced access.
+// * Epilogue I/O goes through TMA (SWIZZLE_128B / SWIZZLE_64B boxes), so no global LSU traffic and no uncoalesced
+//   access: per warp [32 rows x 128 B] in the store/logits epilogues, per CTA [128 rows x 32 columns] boxes issued by
+//   one thread in the pipelined GRU epilogues (epilogue_pipe.cuh).
 #pragma once
 #include "ptx.cuh"
 
@@ -400,14 +401,18 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
 
     if constexpr (EpiTraits<EPI, F32>::kPipe) {
       // ---------------------------------------------------------------- software-pipelined path (epilogue_pipe.cuh)
+      // The four epilogue warps drain a tile together; `leader` issues every TMA operation of the CTA's epilogue.
       constexpr int NCH = BLOCK_N / 32;
       constexpr int SETB = PipeTraits<EPI>::kSetBytes;
       static_assert(NCH % 2 == 0, "ping-pong sets assume an even number of chunks per tile");
-      uint8_t* wsm = smem_epi + ew * (2 * SETB);
-      uint64_t* bar2 = &epi_in_bar[ew * 2];
-      const PipeCtx ctx{&maps, &args, wsm, bar2, lane};
-      auto row_of = [&](int w_) {
-        return ((w_ % tiles_mn) / num_n_tiles) * kTileM * CG + static_cast<int>(cta_rank) * kTileM + ew * 32;
+      static_assert(2 * SETB <= Cfg::kEpiBytes, "epilogue sets do not fit their shared-memory region");
+      uint8_t* wsm = smem_epi;
+      uint64_t* bar2 = &epi_in_bar[0];
+      const PipeCtx ctx{&maps, &args, lane, ew};
+      const bool leader = (ew == 0 && lane == 0);
+      auto epi_sync = [&]() { ptx::named_bar_sync(1, 128); };
+      auto row_of = [&](int w_) {   // first row of this CTA's half of the tile
+        return ((w_ % tiles_mn) / num_n_tiles) * kTileM * CG + static_cast<int>(cta_rank) * kTileM;
       };
       auto n0_of = [&](int w_) { return ((w_ % tiles_mn) % num_n_tiles) * BLOCK_N; };
       auto needs_in = [&](int n0_) { return EPI != EPI_ZR || n0_ >= args.n_split; };
@@ -421,10 +426,15 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
         const int row0 = row_of(w), n0 = n0_of(w);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
-        const bool active = row0 < args.M;
+        const bool active = row0 < args.M;       // CTA-uniform: TMA clips a partially valid tile itself
         const bool tin = needs_in(n0);
         const bool r_tile = (EPI == EPI_ZR) && tin;
         const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+        // this lane's share of the tile's bias (columns [8*lane, 8*lane+8)), fetched while the main loop still runs
+        float breg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if constexpr (EPI == EPI_ZR || EPI == EPI_H) {
+          if (active && lane * 8 < BLOCK_N) load_bias8(args.bias, n0 + lane * 8, 1.0f, breg);
+        }
         SRG_T(tile_t0);
         if (!active) {
           ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -432,7 +442,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
 #pragma unroll 1
           for (int cc = 0; cc < NCH; ++cc) {
             uint8_t* sp = wsm + set * SETB;
-            // the chunk after this one: next chunk of the tile, or chunk 0 of this warp's next (active) tile
+            // the chunk after this one: next chunk of the tile, or chunk 0 of this CTA's next (active) tile
             int nw = w, ncc = cc + 1;
             bool nvalid = true;
             if (ncc == NCH) {
@@ -442,7 +452,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
             }
             const bool pre = nvalid && needs_in(n0_of(nw));
             SRG_T(c0);
-            if (lane == 0 && tin && !issued) {   // only the first chunk of a run is not prefetched
+            if (leader && tin && !issued) {   // only the first chunk of a run is not prefetched
               ptx::tma_wait_group_read<0>();
               pipe_issue<EPI>(ctx, sp, &bar2[set], n0, cc, row0);
             }
@@ -457,7 +467,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
               ph ^= (1u << set);
             }
             SRG_T(c3);
-            if (lane == 0) {
+            if (leader) {
               if (pre) {     // the other set's last stores were committed one iteration ago
                 ptx::tma_wait_group_read<0>();
                 pipe_issue<EPI>(ctx, wsm + (set ^ 1) * SETB, &bar2[set ^ 1], n0_of(nw), ncc, row_of(nw));
@@ -466,16 +476,16 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
               }
             }
             issued = pre;
-            if (!tin) __syncwarp();              // output-only chunk: lanes must not overwrite the set before that wait
+            if (!tin) epi_sync();                // output-only chunk: nobody may overwrite the set before that wait
             SRG_T(c4);
             float accv[32];
             ptx::tmem_ld_32x32(tacc + cc * 32, accv);
             ptx::tmem_ld_wait();
-            pipe_compute<EPI>(ctx, ptx::smem_u32(sp), accv, n0, cc, r_tile);
+            pipe_compute<EPI>(ctx, ptx::smem_u32(sp), accv, breg, cc, r_tile);
             ptx::fence_proxy_async_smem();
-            __syncwarp();
+            epi_sync();                          // the results of all four warps are in the set
             SRG_T(c5);
-            if (lane == 0) {
+            if (leader) {
               pipe_store<EPI>(ctx, sp, n0, cc, row0, r_tile);
               ptx::tma_commit_group();
             }
@@ -501,7 +511,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
       if (lane == 0 && args.epi_t != nullptr)
         for (int i = 0; i < 8; ++i) atomicAdd(&args.epi_t[EPI * 8 + i], tacc_[i]);
 #endif
-      if (lane == 0) ptx::tma_wait_group<0>();
+      if (leader) ptx::tma_wait_group<0>();
       __syncwarp();
     } else
     for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {

@@ -317,10 +317,11 @@ inline int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t st
   bool have_io0 = false;
   for (int i = 0; i < kMaxIoMaps; ++i) {
     if (p.io[i].dtype == DT_NONE || p.io[i].ptr == nullptr) continue;
-    // the software-pipelined epilogues move 32-column chunks (bf16: 64-byte rows), the others 64-column chunks
+    // the software-pipelined epilogues move [128 rows x 32 columns] boxes per CTA (bf16: 64-byte rows), the others
+    // [32 rows x 128 B] boxes per warp
     const bool pipe = !p.f32 && (p.epi == EPI_ZR || p.epi == EPI_H || p.epi == EPI_DH || p.epi == EPI_DRH);
-    SRG_TRY(make_tmap(&maps.io[i], p.io[i].ptr, p.io[i].dtype, p.io[i].rows, p.io[i].cols, p.io[i].ld, 32,
-                      pipe ? 32 : io_box_cols(p.io[i].dtype)));
+    SRG_TRY(make_tmap(&maps.io[i], p.io[i].ptr, p.io[i].dtype, p.io[i].rows, p.io[i].cols, p.io[i].ld,
+                      pipe ? kTileM : 32, pipe ? 32 : io_box_cols(p.io[i].dtype)));
     if (i == 0) have_io0 = true;
   }
   (void)have_io0;
