@@ -132,8 +132,11 @@ class _Engine:
         """First direct-mode backward call of an autograd pass: defer the chain rule through the folded message weights
         and have the autograd engine call finish_backward() when the whole pass has been queued."""
         self.set_deferred(True)
+        task = torch._C._current_graph_task_id()
+        if self._pending is not None and self._pending["task"] != task:
+            self.finish_backward()      # an earlier pass died before its callback ran: settle it first
         if self._pending is None:
-            self._pending = {"grads": grads, "events": []}
+            self._pending = {"grads": grads, "events": [], "task": task}
             torch.autograd.Variable._execution_engine.queue_callback(self.finish_backward)
 
     def backward_mark(self):
