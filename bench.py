@@ -230,8 +230,10 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(k):
             fn()
+        timed.host_issue_ms = (time.perf_counter() - t0) * 1e3   # host time to QUEUE the k steps (no sync inside)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -254,6 +256,7 @@ def run_ours(args):
         sampler.start()
     n0 = lib.srg_launch_count()
     total_ms = timed(run_resident, args.steps)
+    host_issue_ms = timed.host_issue_ms / args.steps
     launches = (lib.srg_launch_count() - n0)
     if use_graph:
         launches = gstep.launches * args.steps
@@ -347,6 +350,8 @@ def run_ours(args):
                            "launch": "cuda_graph_replay" if use_graph else "eager",
                            "l2": "working set per step (GBs of activations) >> 126 MB L2; no explicit flush",
                            "weights": "random-init (reference default init)", "dropout": "train mode, p=0.5"},
+                # host time per step spent queueing the launches: when it approaches ms_per_step the GPU waits for Python
+                "host_issue_ms_per_step": host_issue_ms,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches / args.steps) if args.steps else 0,
                 "roofline": roofline}
         if cb is not None:

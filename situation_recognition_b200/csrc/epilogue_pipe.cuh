@@ -96,7 +96,11 @@ __device__ __forceinline__ void pipe_issue(const PipeCtx& c, uint8_t* sp, uint64
 }
 
 // ---- per-EPI: compute one chunk (all lanes of all four warps) and write the results into the set -------------------
-// s = shared address of the set; breg = this lane's 8 bias values of the tile (columns [8*lane, 8*lane+8) of it)
+// s = shared address of the set; breg = this lane's 8 bias values of the tile (columns [8*lane, 8*lane+8) of it).
+// Each lane owns one row: 32 columns = 4 groups of 8.  The shared-memory accesses are volatile asm, which the compiler
+// keeps in program order, so the code is written in phases -- all loads of a batch of groups, then the math, then the
+// stores -- to have the load latencies overlap instead of paying one per group (a single warp per scheduler runs this,
+// there is nobody to switch to).  GB = groups per batch (register budget: EPI_DH holds five inputs per element).
 template <int EPI>
 __device__ __forceinline__ void pipe_compute(const PipeCtx& c, uint32_t s, const float (&acc)[32],
                                              const float (&breg)[8], int cc, bool r_tile) {
@@ -104,79 +108,110 @@ __device__ __forceinline__ void pipe_compute(const PipeCtx& c, uint32_t s, const
   const int lane = c.lane;
   const uint32_t sf = s + c.ew * kF32Warp;                       // this warp's rows of the fp32 region (offset 0)
   auto sb = [&](int region_off) -> uint32_t { return s + region_off + c.ew * kB16Warp; };
+  if constexpr (EPI == EPI_ZR) {
+    float b[4][8];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if constexpr (EPI == EPI_ZR) {
-      float b[8];
+    for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) b[i] = __shfl_sync(0xffffffffu, breg[i], cc * 4 + g);
-      if (!r_tile) {   // z = sigmoid(acc + b) -> bf16 in region 0 (bf16 layout)
+      for (int i = 0; i < 8; ++i) b[g][i] = __shfl_sync(0xffffffffu, breg[i], cc * 4 + g);
+    if (!r_tile) {   // z = sigmoid(acc + b) -> bf16 in region 0 (bf16 layout)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
         float z[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = act_sigmoid<false>(acc[g * 8 + i] + b[i]);
+        for (int i = 0; i < 8; ++i) z[i] = act_sigmoid<false>(acc[g * 8 + i] + b[g][i]);
         u64_st_bf16x8(s + c.ew * kB16Warp, lane, g, z);
-      } else {         // r = sigmoid(acc + b); rh = r * h
-        float h[8], r[8], rh[8];
-        slot_ld_f32x8(sf, lane, g, h);
+      }
+    } else {         // r = sigmoid(acc + b); rh = r * h
+      float h[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) slot_ld_f32x8(sf, lane, g, h[g]);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float r[8], rh[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          r[i] = act_sigmoid<false>(acc[g * 8 + i] + b[i]);
-          rh[i] = r[i] * h[i];
+          r[i] = act_sigmoid<false>(acc[g * 8 + i] + b[g][i]);
+          rh[i] = r[i] * h[g][i];
         }
         u64_st_bf16x8(sb(kRegB0), lane, g, rh);
         if (a.flags & FLAG_STASH) u64_st_bf16x8(sb(kRegB1), lane, g, r);
       }
-    } else if constexpr (EPI == EPI_H) {
-      float b[8], h[8], z[8], hc[8], hn[8];
+    }
+  } else if constexpr (EPI == EPI_H) {
+    float h[4][8], z[4][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) b[i] = __shfl_sync(0xffffffffu, breg[i], cc * 4 + g);
-      slot_ld_f32x8(sf, lane, g, h);
-      u64_ld_bf16x8(sb(kRegB0), lane, g, z);
+    for (int g = 0; g < 4; ++g) {
+      slot_ld_f32x8(sf, lane, g, h[g]);
+      u64_ld_bf16x8(sb(kRegB0), lane, g, z[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float hc[8], hn[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        hc[i] = act_tanh<false>(acc[g * 8 + i] + b[i]);
-        hn[i] = fmaf(z[i], hc[i] - h[i], h[i]);
+        const float bi = __shfl_sync(0xffffffffu, breg[i], cc * 4 + g);
+        hc[i] = act_tanh<false>(acc[g * 8 + i] + bi);
+        hn[i] = fmaf(z[g][i], hc[i] - h[g][i], h[g][i]);
       }
       slot_st_f32x8(sf, lane, g, hn);                                      // h' fp32, in place
       u64_st_bf16x8(sb(kRegB1), lane, g, hn);                              // h' bf16 operand copy
       if (a.flags & FLAG_STASH) u64_st_bf16x8(sb(kRegB0), lane, g, hc);    // hc over z
-    } else if constexpr (EPI == EPI_DH) {
-      const bool next = (a.flags & FLAG_NEXT) != 0, has_add = (a.flags & FLAG_ADD) != 0;
-      float dh[8];
-      slot_ld_f32x8(sf, lane, g, dh);
+    }
+  } else if constexpr (EPI == EPI_DH) {
+    const bool next = (a.flags & FLAG_NEXT) != 0, has_add = (a.flags & FLAG_ADD) != 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dh[i] += acc[g * 8 + i];
-      if (has_add) {
-        float ad[8];
-        u64_ld_bf16x8(sb(kRegB3), lane, g, ad);
+    for (int g0 = 0; g0 < 4; g0 += 2) {   // two batches of two groups
+      float dh[2][8], ad[2][8], z[2][8], hc[2][8], h[2][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dh[i] += ad[i];
-      }
-      if (next) {
-        float z[8], hc[8], h[8], dz[8], dc[8];
-        u64_ld_bf16x8(sb(kRegB0), lane, g, z);
-        u64_ld_bf16x8(sb(kRegB1), lane, g, hc);
-        u64_ld_bf16x8(sb(kRegB2), lane, g, h);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          dz[i] = dh[i] * (hc[i] - h[i]) * z[i] * (1.0f - z[i]);
-          dc[i] = dh[i] * z[i] * (1.0f - hc[i] * hc[i]);
-          dh[i] = dh[i] * (1.0f - z[i]);
+      for (int j = 0; j < 2; ++j) {
+        slot_ld_f32x8(sf, lane, g0 + j, dh[j]);
+        if (has_add) u64_ld_bf16x8(sb(kRegB3), lane, g0 + j, ad[j]);
+        if (next) {
+          u64_ld_bf16x8(sb(kRegB0), lane, g0 + j, z[j]);
+          u64_ld_bf16x8(sb(kRegB1), lane, g0 + j, hc[j]);
+          u64_ld_bf16x8(sb(kRegB2), lane, g0 + j, h[j]);
         }
-        u64_st_bf16x8(sb(kRegB0), lane, g, dz);
-        u64_st_bf16x8(sb(kRegB1), lane, g, dc);
       }
-      slot_st_f32x8(sf, lane, g, dh);
-    } else {  // EPI_DRH (two bf16 regions, no fp32 one)
-      const uint32_t s0 = s + c.ew * kB16Warp, s1 = s + kB16Box + c.ew * kB16Warp;
-      float h[8], r[8], e[8], dp[8];
-      u64_ld_bf16x8(s0, lane, g, h);
-      u64_ld_bf16x8(s1, lane, g, r);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int g = g0 + j;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dh[j][i] += acc[g * 8 + i];
+        if (has_add) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dh[j][i] += ad[j][i];
+        }
+        if (next) {
+          float dz[8], dc[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            dz[i] = dh[j][i] * (hc[j][i] - h[j][i]) * z[j][i] * (1.0f - z[j][i]);
+            dc[i] = dh[j][i] * z[j][i] * (1.0f - hc[j][i] * hc[j][i]);
+            dh[j][i] = dh[j][i] * (1.0f - z[j][i]);
+          }
+          u64_st_bf16x8(sb(kRegB0), lane, g, dz);
+          u64_st_bf16x8(sb(kRegB1), lane, g, dc);
+        }
+        slot_st_f32x8(sf, lane, g, dh[j]);
+      }
+    }
+  } else {  // EPI_DRH (two bf16 regions, no fp32 one)
+    const uint32_t s0 = s + c.ew * kB16Warp, s1 = s + kB16Box + c.ew * kB16Warp;
+    float h[4][8], r[4][8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      u64_ld_bf16x8(s0, lane, g, h[g]);
+      u64_ld_bf16x8(s1, lane, g, r[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float e[8], dp[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float d = acc[g * 8 + i];
-        dp[i] = d * h[i] * r[i] * (1.0f - r[i]);
-        e[i] = d * r[i];
+        dp[i] = d * h[g][i] * r[g][i] * (1.0f - r[g][i]);
+        e[i] = d * r[g][i];
       }
       u64_st_bf16x8(s0, lane, g, dp);
       u64_st_bf16x8(s1, lane, g, e);

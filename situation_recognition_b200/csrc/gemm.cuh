@@ -105,7 +105,11 @@ __device__ __forceinline__ float act_sigmoid(float x) {
   if constexpr (F32) {
     return 1.0f / (1.0f + expf(-x));
   } else {
-    return __fdividef(1.0f, 1.0f + __expf(-x));
+    // one MUFU op instead of two (ex2 + rcp): sigmoid(x) = 0.5 + 0.5 tanh(x / 2); |error| <= 2.5e-4, below the
+    // bf16 rounding of the stored gate (the epilogue warps are issue/latency bound, see profiles/r01_epi_timing.md)
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
   }
 }
 template <bool F32>

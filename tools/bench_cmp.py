@@ -16,9 +16,10 @@ def main():
     runs = [(p, load(p)) for p in sys.argv[1:]]
     for p, d in runs:
         r = d.get("roofline", {})
-        print("%-40s ms %.3f value %.0f e2e %.0f step_frac %.3f gemm_share %.3f launches %s clocks %s" % (
-            p.split("/")[-1], d["ms_per_step"], d["value"], d["e2e"]["value"], r.get("step_frac", 0),
-            r.get("gemm_share_of_step", 0), d.get("gpu_launches"), d.get("clocks", {}).get("sm_mhz")))
+        print("%-40s ms %.3f (host issue %.3f) value %.0f e2e %.0f step_frac %.3f gemm_share %.3f launches %s clocks %s" % (
+            p.split("/")[-1], d["ms_per_step"], d.get("host_issue_ms_per_step", float("nan")), d["value"],
+            d["e2e"]["value"], r.get("step_frac", 0), r.get("gemm_share_of_step", 0), d.get("gpu_launches"),
+            (d.get("clocks") or {}).get("sm_mhz")))
     names = []
     for _, d in runs:
         for k in d.get("roofline", {}).get("kernels", []):
