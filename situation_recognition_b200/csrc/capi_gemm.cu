@@ -1,5 +1,5 @@
 // C-ABI entry points that expose the raw tcgen05 GEMM (used by the unit tests and the micro-benchmarks).
-#include "host.cuh"
+#include "gemm_launch.cuh"
 #include "../../include/srggnn.h"
 
 using namespace srg;
