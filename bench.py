@@ -25,7 +25,7 @@ if ROOT not in sys.path:
 FLOP_PER_IMAGE_FWD_BWD = 6.547e9   # BASELINE.md section 3 (algorithmic, aggregate-then-project)
 # dram__bytes_read.sum + dram__bytes_write.sum of one noun-path launch (M = 36864) from the `ncu --set full` captures
 # summarised under profiles/ (r01_ncu_full_gru_kernels.md); None = not captured yet
-NCU_TRAFFIC_BYTES = {"gemm_gru_zr_ab": 1.135e9 + 0.435e9, "gemm_gru_h_ab": 0.982e9 + 0.560e9}
+NCU_TRAFFIC_BYTES = {"gemm_gru_zr_ab": 1.067e9 + 0.434e9, "gemm_gru_h_ab": 1.001e9 + 0.559e9}   # profiles/r01_ncu_full_final.md
 METRIC = "ggnn_images_per_sec_fwd_bwd"
 UNIT = "images/s"
 D = 2048
