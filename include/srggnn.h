@@ -113,6 +113,17 @@ int srg_nouns_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_
 int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B, float inv_batch,
                   float* loss, float* dlogits, float grad_scale, const float* stats, void* stream);
 
+/* Backward of the two losses as its own pass: dlogits = grad_scale * (*grad_out) * dLoss/dlogits, where grad_out is
+ * the DEVICE scalar autograd hands to the loss node (nullable = 1).  With these, the forward calls can be given
+ * dlogits = NULL (they then only read the target logits when `stats` is available) and no separate scaling pass over
+ * the [rows, ldl] gradient is needed. */
+int srg_nouns_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_nouns, int B,
+                            const float* counts, const float* grad_out, float grad_scale, float* dlogits,
+                            const float* stats, void* stream);
+int srg_verb_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B,
+                           float inv_batch, const float* grad_out, float grad_scale, float* dlogits,
+                           const float* stats, void* stream);
+
 /* `stats` (nullable) of the two loss calls: the per-column-tile (row max, row sum-exp) pairs the classifier GEMM of the
  * matching forward call left in its workspace, at this byte offset; with them the loss reads each logits row once
  * instead of three times.  They are only valid for the logits that forward call produced. */

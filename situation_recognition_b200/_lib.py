@@ -43,6 +43,8 @@ SIGNATURES = {
     "srg_count_targets": (_i, [_vp, _vp, _i, _vp, _vp]),
     "srg_nouns_loss": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp]),
     "srg_verb_loss": (_i, [_vp, _vp, _i64, _vp, _i, _f, _vp, _vp, _f, _vp, _vp]),
+    "srg_nouns_loss_backward": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp]),
+    "srg_verb_loss_backward": (_i, [_vp, _vp, _i64, _vp, _i, _f, _vp, _f, _vp, _vp, _vp]),
     "srg_workspace_stats_offset": (_sz, [_vp, _i, _i, _i, _i, _vp]),
     "srg_nouns_backward": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _c.POINTER(SrgGrads), _vp, _sz,
                                 _vp]),

@@ -778,7 +778,16 @@ int srg_nouns_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_
                    void* stream) {
   SRG_CHECK(h && logits && gt_nouns && counts && loss, "srg_nouns_loss: null argument");
   SRG_CHECK(ldl >= h->L, "srg_nouns_loss: ldl %lld < n_labels %d", (long long)ldl, h->L);
-  return launch_nouns_ce(logits, ldl, h->L, gt_nouns, B, h->R, counts, loss, dlogits, grad_scale, stats,
+  return launch_nouns_ce(logits, ldl, h->L, gt_nouns, B, h->R, counts, loss, dlogits, grad_scale, nullptr, stats,
+                         h->Lpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
+}
+
+int srg_nouns_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_nouns, int B,
+                            const float* counts, const float* grad_out, float grad_scale, float* dlogits,
+                            const float* stats, void* stream) {
+  SRG_CHECK(h && logits && gt_nouns && counts && dlogits, "srg_nouns_loss_backward: null argument");
+  SRG_CHECK(ldl >= h->L, "srg_nouns_loss_backward: ldl %lld < n_labels %d", (long long)ldl, h->L);
+  return launch_nouns_ce(logits, ldl, h->L, gt_nouns, B, h->R, counts, nullptr, dlogits, grad_scale, grad_out, stats,
                          h->Lpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
 }
 
@@ -786,7 +795,16 @@ int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t
                   float* loss, float* dlogits, float grad_scale, const float* stats, void* stream) {
   SRG_CHECK(h && logits && gt_verb && loss, "srg_verb_loss: null argument");
   SRG_CHECK(ldl >= h->V, "srg_verb_loss: ldl %lld < n_verbs %d", (long long)ldl, h->V);
-  return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, loss, dlogits, grad_scale, stats,
+  return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, loss, dlogits, grad_scale, nullptr, stats,
+                        h->Vpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
+}
+
+int srg_verb_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B,
+                           float inv_batch, const float* grad_out, float grad_scale, float* dlogits,
+                           const float* stats, void* stream) {
+  SRG_CHECK(h && logits && gt_verb && dlogits, "srg_verb_loss_backward: null argument");
+  SRG_CHECK(ldl >= h->V, "srg_verb_loss_backward: ldl %lld < n_verbs %d", (long long)ldl, h->V);
+  return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, nullptr, dlogits, grad_scale, grad_out, stats,
                         h->Vpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
 }
 

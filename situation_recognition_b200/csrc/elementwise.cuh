@@ -48,12 +48,14 @@ int launch_dropout_cast(const float* h32, const uint8_t* keep, float scale, int6
 int launch_dropout_bwd(const float* dx, const uint8_t* keep, float scale, int64_t n, float* dh, cudaStream_t s);
 
 int launch_count_targets(const int64_t* gt, int B, int R, int ignore_index, float* counts, cudaStream_t s);
-// one warp per logits row
+// one warp per logits row; loss and dlogits are both optional; the gradient is scaled by grad_scale and, when
+// gscale_dev is not null, by that device scalar as well
 int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_t* gt, int B, int R,
-                    const float* counts, float* loss, float* dlogits, float grad_scale, const float* stats,
-                    int stats_tiles, cudaStream_t s);
+                    const float* counts, float* loss, float* dlogits, float grad_scale, const float* gscale_dev,
+                    const float* stats, int stats_tiles, cudaStream_t s);
 int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t* gt, int B, float inv_batch,
-                   float* loss, float* dlogits, float grad_scale, const float* stats, int stats_tiles, cudaStream_t s);
+                   float* loss, float* dlogits, float grad_scale, const float* gscale_dev, const float* stats,
+                   int stats_tiles, cudaStream_t s);
 // fp32 [rows, ld] (first n_valid columns) -> bf16 [rows, n_pad], zero padded
 int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, cudaStream_t s);
 

@@ -248,9 +248,11 @@ template <int NT>
 __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, int n_classes, int rows,
                                 const int64_t* __restrict__ gt, int R, int ignore_index,
                                 const float* __restrict__ counts, float inv_fixed, float* __restrict__ loss,
-                                float* __restrict__ dlogits, float grad_scale, const float2* __restrict__ stats,
-                                int stats_tiles) {
+                                float* __restrict__ dlogits, float grad_scale, const float* __restrict__ gscale_dev,
+                                const float2* __restrict__ stats, int stats_tiles) {
   __shared__ float s_loss[kThreads / 32];
+  // gscale_dev: device scalar multiplied into the gradient (the incoming d(loss) of the autograd backward pass)
+  if (gscale_dev != nullptr) grad_scale *= __ldg(gscale_dev);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
   float my_loss = 0.f;
@@ -295,16 +297,37 @@ __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, i
     if (dlogits != nullptr) {
       float* dr = dlogits + static_cast<int64_t>(row) * ldl;
       const float inv_se = 1.0f / se;
-      for (int c = lane; c < ldl; c += 32) {
-        float g = 0.f;
-        if (c < n_classes && wsum != 0.f) {
-          g = wsum * __expf(lr[c] - mx) * inv_se;
+      const float ws = wsum * grad_scale;
+      if ((ldl & 3) == 0 && ((reinterpret_cast<uintptr_t>(lr) | reinterpret_cast<uintptr_t>(dr)) & 15) == 0) {
+        // four columns per lane and access; consecutive iterations are independent, so several loads are in flight
+#pragma unroll 4
+        for (int c = lane * 4; c < ldl; c += 128) {
+          const float4 x = *reinterpret_cast<const float4*>(lr + c);
+          float g[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-          for (int a = 0; a < NT; ++a)
-            if (w[a] != 0.f && tgt[a] == c) g -= w[a];
-          g *= grad_scale;
+          for (int k = 0; k < 4; ++k) {
+            float v = 0.f;
+            if (c + k < n_classes && wsum != 0.f) {
+              v = ws * __expf(g[k] - mx) * inv_se;
+#pragma unroll
+              for (int a = 0; a < NT; ++a)
+                if (w[a] != 0.f && tgt[a] == c + k) v -= w[a] * grad_scale;
+            }
+            g[k] = v;
+          }
+          *reinterpret_cast<float4*>(dr + c) = make_float4(g[0], g[1], g[2], g[3]);
         }
-        dr[c] = g;
+      } else {
+        for (int c = lane; c < ldl; c += 32) {
+          float g = 0.f;
+          if (c < n_classes && wsum != 0.f) {
+            g = ws * __expf(lr[c] - mx) * inv_se;
+#pragma unroll
+            for (int a = 0; a < NT; ++a)
+              if (w[a] != 0.f && tgt[a] == c) g -= w[a] * grad_scale;
+          }
+          dr[c] = g;
+        }
       }
     }
   }
@@ -313,22 +336,36 @@ __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, i
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < warps_per_block; ++i) t += s_loss[i];
-    if (t != 0.f) atomicAdd(loss, t);
+    if (t != 0.f && loss != nullptr) atomicAdd(loss, t);
   }
 }
 
 __global__ void k_cast_pad(const float* __restrict__ src, int64_t ld, int rows, int n_valid, int n_pad,
                            bf16* __restrict__ dst) {
-  const int c2 = n_pad / 2;
-  const int64_t total = static_cast<int64_t>(rows) * c2;
+  // eight columns per thread: two 16-byte loads, one 16-byte store (n_pad is a multiple of 8; ld a multiple of 4)
+  const int c8 = n_pad / 8;
+  const int64_t total = static_cast<int64_t>(rows) * c8;
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(t / c2);
-    const int c = static_cast<int>(t % c2) * 2;
+    const int r = static_cast<int>(t / c8);
+    const int c = static_cast<int>(t % c8) * 8;
     const float* s = src + static_cast<int64_t>(r) * ld;
-    const float a = (c < n_valid) ? s[c] : 0.f;
-    const float b = (c + 1 < n_valid) ? s[c + 1] : 0.f;
-    *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<int64_t>(r) * n_pad + c) = __floats2bfloat162_rn(a, b);
+    float v[8];
+    if (vec && c + 8 <= ld) {
+      const float4 x = *reinterpret_cast<const float4*>(s + c), y = *reinterpret_cast<const float4*>(s + c + 4);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (c + k < n_valid) ? s[c + k] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c + k >= n_valid) v[k] = 0.f;
+    uint4 o;
+    const uint2 lo = pack4_bf16(v[0], v[1], v[2], v[3]), hi = pack4_bf16(v[4], v[5], v[6], v[7]);
+    o.x = lo.x; o.y = lo.y; o.z = hi.x; o.w = hi.y;
+    *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(r) * n_pad + c) = o;
   }
 }
 
@@ -396,57 +433,48 @@ __global__ void k_node_init_bwd(const float* __restrict__ dh0, const bf16* __res
       g.z = (bf16_lo_f(hb.y) > 0.f) ? g.z : 0.f;
       g.w = (bf16_hi_f(hb.y) > 0.f) ? g.w : 0.f;
       const float4 re = *reinterpret_cast<const float4*>(role_emb + static_cast<int64_t>(idx) * D + d);
-      float* dr = d_role_emb + static_cast<int64_t>(idx) * D + d;
-      atomicAdd(dr + 0, g.x * f.x * ve.x);
-      atomicAdd(dr + 1, g.y * f.y * ve.y);
-      atomicAdd(dr + 2, g.z * f.z * ve.z);
-      atomicAdd(dr + 3, g.w * f.w * ve.w);
+      // ~190 embedding rows receive the gradients of B*R node rows: one 16-byte reduction per thread instead of four
+      atomicAdd(reinterpret_cast<float4*>(d_role_emb + static_cast<int64_t>(idx) * D + d),
+                make_float4(g.x * f.x * ve.x, g.y * f.y * ve.y, g.z * f.z * ve.z, g.w * f.w * ve.w));
       accv.x = fmaf(g.x * f.x, re.x, accv.x);
       accv.y = fmaf(g.y * f.y, re.y, accv.y);
       accv.z = fmaf(g.z * f.z, re.z, accv.z);
       accv.w = fmaf(g.w * f.w, re.w, accv.w);
     }
-    float* dv = d_verb_emb + v * D + d;
-    atomicAdd(dv + 0, accv.x);
-    atomicAdd(dv + 1, accv.y);
-    atomicAdd(dv + 2, accv.z);
-    atomicAdd(dv + 3, accv.w);
+    atomicAdd(reinterpret_cast<float4*>(d_verb_emb + v * D + d), accv);
   }
 }
 
-__global__ void k_aggregate_t_bf16(const bf16* __restrict__ dm, const float* __restrict__ mask,
-                                   const bf16* __restrict__ add, int B, int R, int D, bf16* __restrict__ adm) {
+__global__ void __launch_bounds__(kThreads, 4)
+k_aggregate_t_bf16(const bf16* __restrict__ dm, const float* __restrict__ mask, const bf16* __restrict__ add, int B,
+                   int R, int D, bf16* __restrict__ adm) {
   const int D8 = D / 8;
   const int64_t total = static_cast<int64_t>(B) * D8;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int b = static_cast<int>(t / D8);
     const int d = static_cast<int>(t % D8) * 8;
-    float g[kMaxR][8];
+    // the six input rows stay packed as bf16 pairs and are widened where they are used -- as 48 floats they cost 112
+    // registers per thread, which left room for only two blocks per SM (2.6 TB/s)
+    uint4 g[kMaxR];
 #pragma unroll
-    for (int i = 0; i < kMaxR; ++i) {
-      if (i < R) {
-        const uint4 u = *reinterpret_cast<const uint4*>(dm + (static_cast<int64_t>(b) * R + i) * D + d);
-        g[i][0] = bf16_lo_f(u.x); g[i][1] = bf16_hi_f(u.x); g[i][2] = bf16_lo_f(u.y); g[i][3] = bf16_hi_f(u.y);
-        g[i][4] = bf16_lo_f(u.z); g[i][5] = bf16_hi_f(u.z); g[i][6] = bf16_lo_f(u.w); g[i][7] = bf16_hi_f(u.w);
-      }
-    }
+    for (int i = 0; i < kMaxR; ++i)
+      if (i < R) g[i] = *reinterpret_cast<const uint4*>(dm + (static_cast<int64_t>(b) * R + i) * D + d);
     const float* mb = (mask != nullptr) ? mask + static_cast<int64_t>(b) * R * R : nullptr;
 #pragma unroll
     for (int j = 0; j < kMaxR; ++j) {
       if (j < R) {
-        float a[8];
-        {
-          const uint4 u = *reinterpret_cast<const uint4*>(add + (static_cast<int64_t>(b) * R + j) * D + d);
-          a[0] = bf16_lo_f(u.x); a[1] = bf16_hi_f(u.x); a[2] = bf16_lo_f(u.y); a[3] = bf16_hi_f(u.y);
-          a[4] = bf16_lo_f(u.z); a[5] = bf16_hi_f(u.z); a[6] = bf16_lo_f(u.w); a[7] = bf16_hi_f(u.w);
-        }
+        const uint4 ad = *reinterpret_cast<const uint4*>(add + (static_cast<int64_t>(b) * R + j) * D + d);
+        float a[8] = {bf16_lo_f(ad.x), bf16_hi_f(ad.x), bf16_lo_f(ad.y), bf16_hi_f(ad.y),
+                      bf16_lo_f(ad.z), bf16_hi_f(ad.z), bf16_lo_f(ad.w), bf16_hi_f(ad.w)};
 #pragma unroll
         for (int i = 0; i < kMaxR; ++i) {
           if (i < R) {
             const float m = (mb != nullptr) ? __ldg(mb + i * R + j) : 1.0f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] = fmaf(m, g[i][k], a[k]);
+            a[0] = fmaf(m, bf16_lo_f(g[i].x), a[0]); a[1] = fmaf(m, bf16_hi_f(g[i].x), a[1]);
+            a[2] = fmaf(m, bf16_lo_f(g[i].y), a[2]); a[3] = fmaf(m, bf16_hi_f(g[i].y), a[3]);
+            a[4] = fmaf(m, bf16_lo_f(g[i].z), a[4]); a[5] = fmaf(m, bf16_hi_f(g[i].z), a[5]);
+            a[6] = fmaf(m, bf16_lo_f(g[i].w), a[6]); a[7] = fmaf(m, bf16_hi_f(g[i].w), a[7]);
           }
         }
         uint4 o;
@@ -768,37 +796,38 @@ int launch_count_targets(const int64_t* gt, int B, int R, int ignore_index, floa
 }
 
 int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_t* gt, int B, int R,
-                    const float* counts, float* loss, float* dlogits, float grad_scale, const float* stats,
-                    int stats_tiles, cudaStream_t s) {
+                    const float* counts, float* loss, float* dlogits, float grad_scale, const float* gscale_dev,
+                    const float* stats, int stats_tiles, cudaStream_t s) {
   const int rows = B * R;
   if (rows <= 0) return SRG_OK;
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (stats_tiles > 32) stats = nullptr;
   k_cross_entropy<3><<<blocks, kThreads, 0, s>>>(logits, ldl, n_labels, rows, gt, R, n_labels, counts, 0.f, loss,
-                                                dlogits, grad_scale, reinterpret_cast<const float2*>(stats),
-                                                stats_tiles);
+                                                dlogits, grad_scale, gscale_dev,
+                                                reinterpret_cast<const float2*>(stats), stats_tiles);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
 int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t* gt, int B, float inv_batch,
-                   float* loss, float* dlogits, float grad_scale, const float* stats, int stats_tiles,
-                   cudaStream_t s) {
+                   float* loss, float* dlogits, float grad_scale, const float* gscale_dev, const float* stats,
+                   int stats_tiles, cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   int blocks = (B + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (stats_tiles > 32) stats = nullptr;
   k_cross_entropy<1><<<blocks, kThreads, 0, s>>>(logits, ldl, n_verbs, B, gt, 1, -100, nullptr, inv_batch, loss,
-                                                dlogits, grad_scale, reinterpret_cast<const float2*>(stats),
-                                                stats_tiles);
+                                                dlogits, grad_scale, gscale_dev,
+                                                reinterpret_cast<const float2*>(stats), stats_tiles);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
 int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, cudaStream_t s) {
   if (rows <= 0) return SRG_OK;
-  k_cast_pad<<<grid_for(static_cast<int64_t>(rows) * n_pad / 2), kThreads, 0, s>>>(src, ld, rows, n_valid, n_pad, dst);
+  if (n_pad % 8 != 0) return set_error(SRG_ERR_ARG, "cast_pad: padded width %d must be a multiple of 8", n_pad);
+  k_cast_pad<<<grid_for(static_cast<int64_t>(rows) * n_pad / 8), kThreads, 0, s>>>(src, ld, rows, n_valid, n_pad, dst);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }

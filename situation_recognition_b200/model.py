@@ -333,14 +333,16 @@ def _rows_view(logits, n):
 
 
 class _NounsLoss(torch.autograd.Function):
-    """FCGGNN.nouns_loss (model.py:189-201): forward computes the loss and d(loss)/d(logits) in one pass."""
+    """FCGGNN.nouns_loss (model.py:189-201).  Forward only reads what the loss needs (with the classifier's per-tile
+    softmax statistics: the three target logits of a row); the gradient is produced in backward, already multiplied by
+    the incoming d(loss), in one pass over the logits."""
 
     @staticmethod
-    def forward(ctx, model, grad_on, logits, gt_nouns, stats_ptr):
+    def forward(ctx, model, grad_on, logits, gt_nouns, stats):
         eng = model._engine_for(logits.device)
         x, rows, ld = _rows_view(logits, eng.L)
         if x.data_ptr() != logits.data_ptr():
-            stats_ptr = None                       # the logits were copied / converted: the statistics do not apply
+            stats = None                           # the logits were copied / converted: the statistics do not apply
         B = rows // eng.R
         gt = gt_nouns.detach().to(torch.int64).contiguous()
         counts = torch.empty(3, dtype=torch.float32, device=logits.device)
@@ -348,58 +350,60 @@ class _NounsLoss(torch.autograd.Function):
         if model.loss_group is not None:
             torch.distributed.all_reduce(counts, group=model.loss_group)
         loss = torch.zeros((), dtype=torch.float32, device=logits.device)
-        need_grad = grad_on and ctx.needs_input_grad[2]
-        dl = torch.empty(rows, ld, dtype=torch.float32, device=logits.device) if need_grad else None
         _lib.check(eng.lib.srg_nouns_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts), _lib.ptr(loss),
-                                          _lib.ptr(dl), 1.0, ctypes.c_void_p(stats_ptr) if stats_ptr else None,
+                                          None, 1.0, ctypes.c_void_p(stats[1]) if stats else None,
                                           _lib.stream_ptr()))
-        if need_grad:
-            ctx.save_for_backward(dl)
-            ctx.shape = tuple(logits.shape)
-            ctx.n = eng.L
+        if grad_on and ctx.needs_input_grad[2]:
+            ctx.save_for_backward(x, gt, counts)
+            ctx.eng, ctx.geom, ctx.shape, ctx.stats = eng, (rows, ld, B), tuple(logits.shape), stats
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        (dl,) = ctx.saved_tensors
-        g = dl if _is_one(gout) else dl * gout
-        return None, None, g[:, :ctx.n].view(ctx.shape), None, None
+        x, gt, counts = ctx.saved_tensors
+        eng, (rows, ld, B), stats = ctx.eng, ctx.geom, ctx.stats
+        gout = gout.detach().to(torch.float32).contiguous()
+        dl = torch.empty(rows, ld, dtype=torch.float32, device=x.device)
+        _lib.check(eng.lib.srg_nouns_loss_backward(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts),
+                                                   _lib.ptr(gout), 1.0, _lib.ptr(dl),
+                                                   ctypes.c_void_p(stats[1]) if stats else None, _lib.stream_ptr()))
+        ctx.stats = None
+        return None, None, dl[:, :eng.L].view(ctx.shape), None, None
 
 
 class _VerbLoss(torch.autograd.Function):
-    """FCGGNN.verb_loss (model.py:182-187)."""
+    """FCGGNN.verb_loss (model.py:182-187); same split between forward and backward as _NounsLoss."""
 
     @staticmethod
-    def forward(ctx, model, grad_on, logits, gt_verb, stats_ptr):
+    def forward(ctx, model, grad_on, logits, gt_verb, stats):
         eng = model._engine_for(logits.device)
         x, rows, ld = _rows_view(logits, eng.V)
         if x.data_ptr() != logits.data_ptr():
-            stats_ptr = None
+            stats = None
         gt = gt_verb.detach().to(torch.int64).contiguous()
         world = 1
         if model.loss_group is not None:
             world = torch.distributed.get_world_size(model.loss_group)
         loss = torch.zeros((), dtype=torch.float32, device=logits.device)
-        need_grad = grad_on and ctx.needs_input_grad[2]
-        dl = torch.empty(rows, ld, dtype=torch.float32, device=logits.device) if need_grad else None
-        _lib.check(eng.lib.srg_verb_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, 1.0 / (rows * world),
-                                         _lib.ptr(loss), _lib.ptr(dl), 1.0,
-                                         ctypes.c_void_p(stats_ptr) if stats_ptr else None, _lib.stream_ptr()))
-        if need_grad:
-            ctx.save_for_backward(dl)
-            ctx.shape = tuple(logits.shape)
-            ctx.n = eng.V
+        inv = 1.0 / (rows * world)
+        _lib.check(eng.lib.srg_verb_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, inv, _lib.ptr(loss), None, 1.0,
+                                         ctypes.c_void_p(stats[1]) if stats else None, _lib.stream_ptr()))
+        if grad_on and ctx.needs_input_grad[2]:
+            ctx.save_for_backward(x, gt)
+            ctx.eng, ctx.geom, ctx.shape, ctx.stats = eng, (rows, ld, inv), tuple(logits.shape), stats
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        (dl,) = ctx.saved_tensors
-        g = dl if _is_one(gout) else dl * gout
-        return None, None, g[:, :ctx.n].view(ctx.shape), None, None
-
-
-def _is_one(g):
-    return False  # keep the general path; a fused scale is a later optimisation
+        x, gt = ctx.saved_tensors
+        eng, (rows, ld, inv), stats = ctx.eng, ctx.geom, ctx.stats
+        gout = gout.detach().to(torch.float32).contiguous()
+        dl = torch.empty(rows, ld, dtype=torch.float32, device=x.device)
+        _lib.check(eng.lib.srg_verb_loss_backward(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, inv, _lib.ptr(gout), 1.0,
+                                                  _lib.ptr(dl), ctypes.c_void_p(stats[1]) if stats else None,
+                                                  _lib.stream_ptr()))
+        ctx.stats = None
+        return None, None, dl[:, :eng.V].view(ctx.shape), None, None
 
 
 def _has_batchnorm_in_train(module):
@@ -553,13 +557,14 @@ class FCGGNN(nn.Module):
 
     @staticmethod
     def _stats_ptr(logits, expected_rows_stride):
-        """Device pointer of the classifier's per-tile softmax statistics if `logits` is the very tensor a predict_*
-        call of this model returned (same storage, same layout), else None."""
+        """(workspace tensor, device pointer) of the classifier's per-tile softmax statistics if `logits` is the very
+        tensor a predict_* call of this model returned (same storage, same layout), else None.  The loss node keeps
+        the pair, so the workspace outlives it."""
         st = getattr(logits, "_srg_stats", None)
         if st is None or logits.dtype != torch.float32 or logits.stride(-1) != 1 or \
                 logits.stride(-2) != expected_rows_stride:
             return None
-        return st[1]
+        return st
 
     def verb_loss(self, pred_verb, gt_verb):
         eng_pad = _pad256(self.encoder.get_num_verbs())
