@@ -381,3 +381,28 @@ def test_ragged_batches_train_step(enc_syn, B):
     if torch.equal(mpv.argmax(-1).cpu(), pv.argmax(-1)):
         for k, p in m.named_parameters():
             assert relmax(p.grad, grads[k]) <= 3e-2, k
+
+
+def test_loss_backward_scales_with_incoming_gradient(enc_syn):
+    """The loss nodes produce d(loss)/d(logits) in backward and multiply it by the incoming gradient (a device scalar)
+    in the same pass: backpropagating 2.5 * verb_loss + 0.5 * nouns_loss must give exactly that combination."""
+    B, D = 16, 256
+    params = O.init_params(504, 190, 2001, D, seed=2)
+    fv, fn, gt_verb, gt_nouns = [x.cuda() for x in make_batch(enc_syn, B, D, seed=21)]
+    grads = []
+    for wv, wn in ((1.0, 0.0), (0.0, 1.0), (2.5, 0.5)):
+        m = model_from(params, enc_syn, D, "bf16").eval()
+        pv, pn, _ = m(fv, gt_verb, img_nouns=fn)
+        (wv * m.verb_loss(pv, gt_verb) + wn * m.nouns_loss(pn, gt_nouns)).backward()
+        grads.append({k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in m.named_parameters()})
+    gv, gn, gc = grads
+    for k in gc:
+        want = 2.5 * gv[k] + 0.5 * gn[k]
+        assert relmax(gc[k], want) <= 2e-3, k
+    # a detached copy of the logits has no classifier statistics attached: same loss value through the 3-pass path
+    m = model_from(params, enc_syn, D, "bf16").eval()
+    with torch.no_grad():
+        pv, pn, _ = m(fv, gt_verb, img_nouns=fn)
+        a, b = m.nouns_loss(pn, gt_nouns).item(), m.nouns_loss(pn.clone(), gt_nouns).item()
+        c, d = m.verb_loss(pv, gt_verb).item(), m.verb_loss(pv.clone(), gt_verb).item()
+    assert abs(a - b) <= 1e-5 * abs(b) and abs(c - d) <= 1e-5 * abs(d)
