@@ -397,8 +397,8 @@ def test_loss_backward_scales_with_incoming_gradient(enc_syn):
         grads.append({k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in m.named_parameters()})
     gv, gn, gc = grads
     for k in gc:
-        want = 2.5 * gv[k] + 0.5 * gn[k]
-        assert relmax(gc[k], want) <= 2e-3, k
+        want = 2.5 * gv[k] + 0.5 * gn[k]          # the two passes round their bf16 intermediates independently
+        assert relmax(gc[k], want) <= 1e-2, k
     # a detached copy of the logits has no classifier statistics attached: same loss value through the 3-pass path
     m = model_from(params, enc_syn, D, "bf16").eval()
     with torch.no_grad():
