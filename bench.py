@@ -195,7 +195,8 @@ def run_ours(args):
         model._engine_for(dev).set_cta_group(args.cta_group)
     flat = parallel.attach(model, flat_params=True)
     # kernels are launched eagerly by default: with the verb path overlapped on a side stream the GPU never waits for
-    # the host (measured: graph replay 31.89 ms vs eager 31.87 ms at B=6144; 5.96 vs 5.84 ms at 8 x 768).  --graph
+    # the host at B=6144 (graph replay 31.89 ms vs eager 31.87 ms); at 8 x 768 the host needs 3.3 of the 5.3 ms to queue
+    # a step and the graph is 1.8 % faster (5.30 vs 5.39 ms) -- not enough to make it the default.  --graph
     # replays the whole step (NCCL all-reduce included) from one CUDA graph instead.
     use_graph = args.graph and not args.no_graph
     opt = parallel.FlatAdamax(flat, lr=0.002, max_norm=1.0)      # sr.py:80-83,472-473 as one fused kernel

@@ -44,10 +44,8 @@ def main():
         packs = [i for i, (_, k, _) in enumerate(rows) if k == "k_pack_weight_multi"]
         # a step opens with the weight repack (two pack launches a few kernels apart)
         starts = [i for n, i in enumerate(packs) if n == 0 or i - packs[n - 1] > 8]
-        for n, i in enumerate(starts):
-            while i > 0 and rows[i - 1][1].startswith("torch:") and "Fill" in rows[i - 1][1] + "Fill":
-                if "ill" not in rows[i - 1][1]:
-                    break
+        for n, i in enumerate(starts):     # a step's zero-fills precede its first weight-pack launch
+            while i > 0 and rows[i - 1][1].startswith("torch:") and "Fill" in rows[i - 1][1]:
                 i -= 1
             starts[n] = i
         if len(starts) >= 2:
