@@ -345,10 +345,18 @@ class _NounsLoss(torch.autograd.Function):
             stats = None                           # the logits were copied / converted: the statistics do not apply
         B = rows // eng.R
         gt = gt_nouns.detach().to(torch.int64).contiguous()
-        counts = torch.empty(3, dtype=torch.float32, device=logits.device)
-        _lib.check(eng.lib.srg_count_targets(eng.h, _lib.ptr(gt), B, _lib.ptr(counts), _lib.stream_ptr()))
-        if model.loss_group is not None:
-            torch.distributed.all_reduce(counts, group=model.loss_group)
+        # the denominators depend on the targets only: nouns_loss(pred_nouns, gt) and nouns_loss(gt_pred_nouns, gt) of
+        # one step (sr.py:69-70) share them, which also halves the small all-reduces of a sharded step
+        key = (gt.data_ptr(), gt._version, tuple(gt.shape), torch.cuda.current_stream(gt.device).cuda_stream)
+        cached = model._counts_cache
+        if cached is not None and cached[0] == key:
+            counts = cached[1]
+        else:
+            counts = torch.empty(3, dtype=torch.float32, device=logits.device)
+            _lib.check(eng.lib.srg_count_targets(eng.h, _lib.ptr(gt), B, _lib.ptr(counts), _lib.stream_ptr()))
+            if model.loss_group is not None:
+                torch.distributed.all_reduce(counts, group=model.loss_group)
+            model._counts_cache = (key, counts, gt)     # holding gt keeps its address from being reused
         loss = torch.zeros((), dtype=torch.float32, device=logits.device)
         _lib.check(eng.lib.srg_nouns_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts), _lib.ptr(loss),
                                           None, 1.0, ctypes.c_void_p(stats[1]) if stats else None,
@@ -461,6 +469,7 @@ class FCGGNN(nn.Module):
         self.overlap_streams = True      # run the verb path on a side stream (see forward)
         self._flat = None                # parallel.attach(): flat gradient / parameter buffers
         self._last_stats = None
+        self._counts_cache = None        # (key, counts, targets) of the last nouns_loss call
 
     # sr.py accesses model.module.* when CUDA is available (DataParallel wrapper in the reference)
     @property
