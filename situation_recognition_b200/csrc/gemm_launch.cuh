@@ -1,6 +1,7 @@
 // GEMM launcher: maps a problem description onto one gemm_kernel instantiation (descriptor encoding + dispatch).
 // Included by exactly one translation unit (capi_gemm.cu); everybody else calls run_gemm() declared in host.cuh.
 #pragma once
+#include <cstdlib>
 #include "host.cuh"
 
 namespace srg {
@@ -180,6 +181,9 @@ int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t stream) {
   args.n_valid = p.n_valid;
   args.stats = p.stats;
   args.flags = p.flags;
+  // weights stay in L2 (evict_last) unless SRG_B_EVICT_LAST=0; the weight-gradient GEMMs have activations on both sides
+  static const bool b_evict_last = [] { const char* v = getenv("SRG_B_EVICT_LAST"); return !(v && v[0] == '0'); }();
+  args.b_hint = (b_evict_last && !(p.a_mn && p.b_mn)) ? 0x14F0000000000000ull : 0ull;
 #ifdef SRG_EPI_TIMING
   if (g_epi_t_dev == nullptr) {
     SRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_epi_t_dev), 64 * sizeof(unsigned long long)));

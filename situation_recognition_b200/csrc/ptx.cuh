@@ -170,6 +170,29 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
                : "memory");
 }
 
+// ---- the same three with an L2 eviction-priority hint (createpolicy encodings: evict_first for data that is streamed
+// once, evict_last for operands every CTA re-reads); hint == 0 selects the plain instruction
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1,
+                                            uint64_t hint) {
+  if (hint == 0) return tma_load_2d(m, bar, smem, c0, c1);
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1,
+                                                 uint64_t hint) {
+  if (hint == 0) return tma_load_2d_pair(m, bar, smem, c0, c1);
+  uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 __device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
 template <int N>
