@@ -1,7 +1,7 @@
 """Headline benchmark: GGNN role-graph stage, images/sec forward+backward (BASELINE.json).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --steps K --warmup W     # CPU arm: the oracle port of the reference
+    python bench.py --impl reference --steps K --warmup W     # CPU arm: the UNMODIFIED reference (baseline/_ref)
 
 Workload (BASELINE.json configs[2]/[3]): one training step of the GGNN stage at global batch 6144, D=2048,
 504 verbs / 190 roles / 2001 labels / 6 roles, synthetic backbone features and labels, random-init weights:
@@ -108,24 +108,43 @@ def oracle_step(O, enc, params, batch, tables):
     return O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, enc.get_num_labels())
 
 
-def cpu_baseline(budget_s=20.0):
-    """The oracle port of the reference's fwd+bwd step, timed on this host's cores on a bounded sample."""
+REF_SAMPLE = 64      # images per CPU step: a fixed, bounded sample of the 6144-image step (same at every N)
+
+
+def reference_runner(sample):
+    """(callable running ONE CPU training step on `sample` images, kind, description).
+
+    kind "reference": the unmodified reference classes from the git-ignored copy baseline/_ref (FCGGNN.forward +
+    verb_loss + nouns_loss + backward + clip_grad_norm_ + Adamax, sr.py:63-83, backbones replaced by Identity so the
+    input is the [B, 2048] feature matrix).  kind "port": the oracle restatement, when no reference copy travelled."""
     import torch
-    B = 32
-    O, enc, params, batch, tables = oracle_setup(B)
+    from oracle import ref_harness
+    from situation_recognition_b200.synthetic import make_batch, make_train_json
+    if ref_harness.available():
+        st = ref_harness.ReferenceStep(make_train_json(seed=0), D=D, seed=0)
+        _, fn, gt_verb, gt_nouns = make_batch(st.encoder, sample, D, seed=1234)
+        return (lambda: st(fn, gt_verb, gt_nouns)), "reference", \
+            "unmodified reference (baseline/_ref: FCGGNN.forward + losses + backward + clip + Adamax, sr.py:63-83, fp32)"
+    O, enc, params, batch, tables = oracle_setup(sample)
+    return (lambda: oracle_step(O, enc, params, batch, tables)), "port", \
+        "oracle port of the reference arithmetic (no baseline/_ref copy on this box), fwd+bwd, fp32"
+
+
+def cpu_baseline(steps=8):
+    """The reference's CPU implementation of the step, timed on this host's cores on a bounded sample (~10-30 s)."""
+    import torch
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    run, kind, what = reference_runner(REF_SAMPLE)
+    run()
     t0 = time.time()
-    oracle_step(O, enc, params, batch, tables)
-    t1 = time.time() - t0
-    # pick a sample that fills roughly the budget
-    per_img = t1 / B
-    Bs = int(max(32, min(256, (budget_s / 2) / max(per_img, 1e-6))) // 8 * 8)
-    O, enc, params, batch, tables = oracle_setup(Bs)
-    t0 = time.time()
-    oracle_step(O, enc, params, batch, tables)
-    dt = time.time() - t0
-    return {"value": Bs / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "1 fwd+bwd step of the oracle port (reference arithmetic as written, fp32) on %d images; "
-                      "os.cpu_count()=%s" % (Bs, os.cpu_count())}
+    n = 0
+    while n < steps and (n < 2 or time.time() - t0 < 25.0):
+        run()
+        n += 1
+    dt = (time.time() - t0) / n
+    return {"value": REF_SAMPLE / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%d steps of %d images each (of the 6144-image step) after 1 warm-up: %s; os.cpu_count()=%s"
+                      % (n, REF_SAMPLE, what, os.cpu_count())}
 
 
 def run_reference(args):
@@ -133,30 +152,26 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core, the same count at every N
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     steps, warmup = args.steps, args.warmup
-    O, enc, params, batch, tables = oracle_setup(8)
-    t0 = time.time()
-    oracle_step(O, enc, params, batch, tables)
-    per_img = (time.time() - t0) / 8
-    budget = 150.0
-    Bs = int(max(8, min(256, budget / max(1, steps + warmup) / max(per_img, 1e-6))) // 8 * 8)
-    O, enc, params, batch, tables = oracle_setup(Bs)
+    run, kind, what = reference_runner(REF_SAMPLE)
     for _ in range(warmup):
-        oracle_step(O, enc, params, batch, tables)
+        run()
     t0 = time.time()
     for _ in range(steps):
-        oracle_step(O, enc, params, batch, tables)
+        run()
     dt = (time.time() - t0) / max(1, steps)
-    value = Bs / dt
-    cb = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-          "sample": "each step = fwd+bwd of the oracle port on %d images (bounded sample of the 6144-image step)" % Bs}
+    value = REF_SAMPLE / dt
+    cb = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+          "sample": "each step = %d images (fixed bounded sample of the 6144-image step): %s" % (REF_SAMPLE, what)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ggnn_stage_fwd_bwd", "global_batch": args.batch, "sample_batch": Bs, "D": D,
-                       "verbs": 504, "roles": 190, "labels": 2001, "max_roles": 6, "T": 4},
+            "config": {"workload": "ggnn_stage_fwd_bwd (BASELINE.json configs[2]; sharded = configs[3])",
+                       "global_batch": args.batch, "sample_batch": REF_SAMPLE, "D": D,
+                       "verbs": 504, "roles": 190, "labels": 2001, "max_roles": 6, "T": 4,
+                       "step": "zero_grad+fwd(verb,pred-noun,gt-noun)+3 losses+bwd+clip+adamax"},
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -178,12 +193,13 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the GGNN stage (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # The bench prints exactly ONE line on stdout.  NCCL_DEBUG stays as the caller set it (the driver counts the
+    # communicator's ranks in NCCL's INFO lines): everything that is written to fd 1 while the bench runs -- NCCL's banner
+    # and INFO lines included -- is redirected to stderr, and the result line goes to the saved stdout at the end.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # the bench prints exactly one line on stdout: keep NCCL's own banner ("NCCL version ...") off it
-        if "SRG_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["SRG_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -194,11 +210,11 @@ def run_ours(args):
     if args.cta_group:
         model._engine_for(dev).set_cta_group(args.cta_group)
     flat = parallel.attach(model, flat_params=True)
-    # kernels are launched eagerly by default: with the verb path overlapped on a side stream the GPU never waits for
-    # the host at B=6144 (graph replay 31.89 ms vs eager 31.87 ms); at 8 x 768 the host needs 3.3 of the 5.3 ms to queue
-    # a step and the graph is 1.8 % faster (5.30 vs 5.39 ms) -- not enough to make it the default.  --graph
-    # replays the whole step (NCCL all-reduce included) from one CUDA graph instead.
-    use_graph = args.graph and not args.no_graph
+    # One GPU: kernels are launched eagerly (with the verb path overlapped on a side stream the GPU never waits for the
+    # host at B=6144: graph replay 31.89 ms vs eager 31.87 ms).  Sharded runs replay the whole step (NCCL collectives
+    # included) from one CUDA graph: at 8 x 768 images the host needs most of the step time to queue the launches.
+    # --graph / --no-graph override.
+    use_graph = (args.graph or world > 1) and not args.no_graph
     opt = parallel.FlatAdamax(flat, lr=0.002, max_norm=1.0)      # sr.py:80-83,472-473 as one fused kernel
     params = [p for p in model.parameters() if p.requires_grad]
 
@@ -210,8 +226,11 @@ def run_ours(args):
     resident = [x.to(dev, non_blocking=True) for x in host]
     h2d_bytes = sum(x.numel() * x.element_size() for x in host)
 
+    model.global_batch = Bg        # the sharded verb loss divides by the global batch without an extra all-reduce
+
     def step(inputs):
         a, b, v, n = inputs
+        model._counts_cache = None      # a real loop sees new labels every step: count (and all-reduce) them every step
         flat.zero()
         pred_verb, pred_nouns, gt_pred_nouns = model(a, v, img_nouns=b)
         vl = model.verb_loss(pred_verb, v)
@@ -252,6 +271,17 @@ def run_ours(args):
         run_resident = lambda: step(resident)
     for _ in range(max(3, args.warmup)):
         run_resident()
+    # pre-heat: the same step, back to back for >= args.preheat seconds, so that the timed region starts in the
+    # sustained clock / power state at every N (a 0.1 s window after an idle GPU runs at boost clocks)
+    t_probe = timed(run_resident, 2) / 2
+    n_heat = int(max(0.0, args.preheat) * 1e3 / max(t_probe, 1e-3)) + 1 if args.preheat > 0 else 0
+    t_heat0 = time.perf_counter()
+    for i in range(n_heat):
+        run_resident()
+        if (i & 15) == 15:
+            torch.cuda.current_stream().synchronize()        # keep the launch queue bounded
+    torch.cuda.synchronize()
+    preheat_s = time.perf_counter() - t_heat0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -293,6 +323,8 @@ def run_ours(args):
                 "traffic": NCU_TRAFFIC_BYTES.get(top["kernel"]) if Bl == 6144 else None,
                 "traffic_note": "bytes of one noun-path launch (M=36864) of this kernel, ncu --set full, profiles/",
                 "peak_source": peaks["source"] + " (sustained bf16; burst %.1f)" % peaks["bf16_burst"],
+                "peak_burst": peaks["bf16_burst"], "frac_burst": top["tflops"] / peaks["bf16_burst"],
+                "step_frac_burst": value * FLOP_PER_IMAGE_FWD_BWD / 1e12 / world / peaks["bf16_burst"],
                 "launch_ms": top["ms_per_step"] / top["launches_per_step"],
                 "share_of_step": top["ms_per_step"] / ms_per_step,
                 # per-GPU figures (the whole-job value divided by the number of GPUs)
@@ -349,6 +381,8 @@ def run_ours(args):
                            "max_roles": 6, "T": 4, "parallelism": "dp%d" % world,
                            "step": "zero_grad+fwd(verb,pred-noun,gt-noun)+3 losses+bwd+allreduce+clip+adamax",
                            "launch": "cuda_graph_replay" if use_graph else "eager",
+                           "preheat_s": round(preheat_s, 2), "preheat_steps": n_heat,
+                           "timed_region_s": round(total_ms / 1e3, 3),
                            "l2": "working set per step (GBs of activations) >> 126 MB L2; no explicit flush",
                            "weights": "random-init (reference default init)", "dropout": "train mode, p=0.5"},
                 # host time per step spent queueing the launches: when it approaches ms_per_step the GPU waits for Python
@@ -357,7 +391,7 @@ def run_ours(args):
                 "roofline": roofline}
         if cb is not None:
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         # leave without running NCCL / CUDA-graph destructors: a captured or in-flight communicator has been seen to
         # block interpreter shutdown after the result line was already printed
@@ -376,6 +410,7 @@ def main():
     ap.add_argument("--batch", type=int, default=6144, help="global batch (BASELINE.json: 6144)")
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--preheat", type=float, default=3.0, help="seconds of untimed back-to-back steps before timing")
     ap.add_argument("--graph", action="store_true", help="replay the whole training step from one CUDA graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -27,7 +27,9 @@ typedef struct srg_handle srg_handle;
 enum { SRG_DT_F32 = 1, SRG_DT_BF16 = 2 };
 /* arithmetic of the tensor-core contractions:
  *   SRG_PREC_BF16 : bf16 operands, fp32 accumulate (training / throughput mode)
- *   SRG_PREC_FP32 : 3-term bf16 split (hi*hi + hi*lo + lo*hi), fp32 accumulate -- fp32-parity mode, forward only */
+ *   SRG_PREC_FP32 : every operand split into three bf16 parts x = hi + mid + lo, a product expanded into the six terms
+ *                   of weight >= 2^-16 (hi*hi + hi*mid + mid*hi + hi*lo + lo*hi + mid*mid), fp32 accumulate --
+ *                   fp32-parity mode, forward only */
 enum { SRG_PREC_BF16 = 0, SRG_PREC_FP32 = 1 };
 /* GGSNN.forward(..., verb=True|False), model.py:59-77 */
 enum { SRG_MODE_NOUN = 0, SRG_MODE_VERB = 1 };
@@ -36,7 +38,8 @@ const char* srg_last_error(void);
 int srg_version(void);
 
 /* FCGGNN.__init__ (model.py:90-111): D = hidden size (2048), R = encoder.get_max_role_count() (6), T = 4 (model.py:60),
- * n_verbs/n_roles/n_labels = encoder.get_num_{verbs,roles,labels}().  `cta_group` = 1 or 2 CTAs per tcgen05.mma. */
+ * n_verbs/n_roles/n_labels = encoder.get_num_{verbs,roles,labels}().  srg_set_cta_group selects 1 or 2 CTAs per
+ * tcgen05.mma (default 2: M=256 x N=256 tiles on a CTA pair; 1 = 128 x 128 tiles, kept for tests). */
 int srg_create(srg_handle** out, int device, int D, int R, int T, int n_verbs, int n_roles, int n_labels);
 int srg_destroy(srg_handle* h);
 int srg_set_cta_group(srg_handle* h, int cta_group);
@@ -84,8 +87,8 @@ size_t srg_workspace_bytes(srg_handle* h, int mode, int B, int precision, int sa
 /* predict_nouns minus the backbone (model.py:117-155):
  *   role gather + mask (117,147) -> node = relu(feat * role_emb[role_idx] * verb_emb[verb]) (124-144)
  *   -> GGSNN(node, mask) (151) -> Dropout + Linear (152) -> logits[B*R, ldl] (first n_labels columns valid).
- * feat: fp32 [B, D]; verb: int64 [B]; keep: uint8 [B*R, D] dropout keep-mask or NULL (eval / p == 0);
- * out_role_idx / out_mask are optional copies of the gather results (NULL to skip). */
+ * feat: fp32 [B, D]; verb: int64 [B]; keep: uint8 [B*R, D] dropout keep-mask or NULL (eval / p == 0).
+ * The gathered role ids / mask stay inside the workspace; srg_gather_mask returns them when a caller wants them. */
 int srg_nouns_forward(srg_handle* h, const float* feat, const int64_t* verb, int B, const float* role_emb,
                       const float* verb_emb, const uint8_t* keep, float drop_p, float* logits, int64_t ldl,
                       int precision, int save_for_backward, void* workspace, size_t workspace_bytes, void* stream);
@@ -109,9 +112,13 @@ int srg_nouns_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_
                    const float* counts, float* loss, float* dlogits, float grad_scale, const float* stats,
                    void* stream);
 
-/* FCGGNN.verb_loss (model.py:182-187): CrossEntropy(pred_verb[B, n_verbs], gt_verb[B]), mean over inv_batch = 1/B_global. */
+/* FCGGNN.verb_loss (model.py:182-187): CrossEntropy(pred_verb[B, n_verbs], gt_verb[B]); the mean is taken over the
+ * GLOBAL batch: inv_batch = 1/B_global, or -- when batch_total (device fp32 scalar, nullable) is given -- 1 / *batch_total,
+ * which lets a sharded caller all-reduce its local batch sizes on the stream without a host synchronisation (shards
+ * of unequal size: the tail batch of an epoch). */
 int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B, float inv_batch,
-                  float* loss, float* dlogits, float grad_scale, const float* stats, void* stream);
+                  const float* batch_total, float* loss, float* dlogits, float grad_scale, const float* stats,
+                  void* stream);
 
 /* Backward of the two losses as its own pass: dlogits = grad_scale * (*grad_out) * dLoss/dlogits, where grad_out is
  * the DEVICE scalar autograd hands to the loss node (nullable = 1).  With these, the forward calls can be given
@@ -121,8 +128,8 @@ int srg_nouns_loss_backward(srg_handle* h, const float* logits, int64_t ldl, con
                             const float* counts, const float* grad_out, float grad_scale, float* dlogits,
                             const float* stats, void* stream);
 int srg_verb_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B,
-                           float inv_batch, const float* grad_out, float grad_scale, float* dlogits,
-                           const float* stats, void* stream);
+                           float inv_batch, const float* batch_total, const float* grad_out, float grad_scale,
+                           float* dlogits, const float* stats, void* stream);
 
 /* `stats` (nullable) of the two loss calls: the per-column-tile (row max, row sum-exp) pairs the classifier GEMM of the
  * matching forward call left in its workspace, at this byte offset; with them the loss reads each logits row once

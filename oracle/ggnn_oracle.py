@@ -128,10 +128,17 @@ def predict_verb(params, feat, keep=None, drop_p=0.5):
                   params["verb_classifier.1.bias"])                                      # :168
 
 
-def forward(params, feat_verbs, feat_nouns, gt_verb, verb2roles, role_count, keeps=(None, None, None), drop_p=0.5):
-    """model.py:171-180.  keeps = dropout keep-masks for (verb path, predicted-verb noun path, gt-verb noun path)."""
+def forward(params, feat_verbs, feat_nouns, gt_verb, verb2roles, role_count, keeps=(None, None, None), drop_p=0.5,
+            pred_verbs=None):
+    """model.py:171-180.  keeps = dropout keep-masks for (verb path, predicted-verb noun path, gt-verb noun path).
+
+    pred_verbs (test infrastructure, not in the reference): verb ids to condition the predicted-verb noun path on
+    instead of argmax(pred_verb).  With random-init weights the verb logits are nearly tied, so bf16 arithmetic flips
+    ~1 % of the argmaxes; feeding the CUDA path's own predictions keeps the two role graphs identical and makes the
+    pred-noun logits / gradients comparable row by row."""
     pred_verb = predict_verb(params, feat_verbs, keeps[0], drop_p)                       # :175
-    pred_nouns = predict_nouns(params, feat_nouns, torch.argmax(pred_verb, 1), verb2roles, role_count,
+    verbs = torch.argmax(pred_verb, 1) if pred_verbs is None else pred_verbs
+    pred_nouns = predict_nouns(params, feat_nouns, verbs, verb2roles, role_count,
                                keeps[1], drop_p)                                         # :176-177
     gt_pred_nouns = predict_nouns(params, feat_nouns, gt_verb, verb2roles, role_count, keeps[2], drop_p)  # :178
     return pred_verb, pred_nouns, gt_pred_nouns
@@ -179,14 +186,54 @@ def init_params(num_verbs, num_roles, num_labels, D, seed=0, dtype=torch.float32
 
 
 def train_step_grads(params, feat_verbs, feat_nouns, gt_verb, gt_nouns, verb2roles, role_count, num_labels,
-                     keeps=(None, None, None), drop_p=0.5):
+                     keeps=(None, None, None), drop_p=0.5, pred_verbs=None):
     """sr.py:63-79 without AMP: loss = verb_loss + nouns_loss(pred path); returns (losses, grads dict).
     gt_nouns_loss is computed but not back-propagated (sr.py:70,76)."""
     ps = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
-    pv, pn, gpn = forward(ps, feat_verbs, feat_nouns, gt_verb, verb2roles, role_count, keeps, drop_p)
+    pv, pn, gpn = forward(ps, feat_verbs, feat_nouns, gt_verb, verb2roles, role_count, keeps, drop_p, pred_verbs)
     vl = verb_loss(pv, gt_verb)
     nl = nouns_loss(pn, gt_nouns, num_labels)
     gl = nouns_loss(gpn, gt_nouns, num_labels)
     (vl + nl).backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in ps.items()}
     return (vl.detach(), nl.detach(), gl.detach()), grads, (pv.detach(), pn.detach(), gpn.detach())
+
+
+def train_step_grads_chunked(params, feat_verbs, feat_nouns, gt_verb, gt_nouns, verb2roles, role_count, num_labels,
+                             keeps=(None, None, None), drop_p=0.5, pred_verbs=None, chunk=256, shard=None,
+                             keep_logits=False):
+    """The same step as train_step_grads on a batch too large for one pass of the as-written arithmetic (the
+    [B,6,6,D] expansion of model.py:67-73 is 1.8 GB per copy at B = 6144): the batch is processed in chunks of `chunk`
+    images with the GLOBAL loss denominators (B for the verb loss, the non-ignored target counts per annotation for
+    the noun losses, model.py:184-185,196-199) and the gradients are summed, which is what one full-batch backward
+    computes.  shard = (lo, hi) restricts the sums to that slice of the batch while keeping the global denominators
+    (the per-rank share of a data-parallel step, sr.py:66-76 on GPU 0 of the reference's DataParallel)."""
+    B = feat_verbs.shape[0]
+    lo, hi = (0, B) if shard is None else shard
+    counts = [(gt_nouns[:, a] != num_labels).sum().clamp_min(1).to(torch.float32) for a in range(3)]
+    ps = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    tot = torch.zeros(3, dtype=torch.float64)
+    logits = ([], [], [])
+    for c0 in range(lo, hi, chunk):
+        c1 = min(hi, c0 + chunk)
+        sl = slice(c0, c1)
+        kp = tuple(None if k is None else k[(c0 if i == 0 else c0 * verb2roles.shape[1]):
+                                            (c1 if i == 0 else c1 * verb2roles.shape[1])] for i, k in enumerate(keeps))
+        pvb = None if pred_verbs is None else pred_verbs[sl]
+        pv, pn, gpn = forward(ps, feat_verbs[sl], feat_nouns[sl], gt_verb[sl], verb2roles, role_count, kp, drop_p, pvb)
+        vl = F.cross_entropy(pv, gt_verb[sl], reduction="sum") / B
+        nl, gl = 0, 0
+        for a in range(3):
+            nl = nl + F.cross_entropy(pn.transpose(1, 2), gt_nouns[sl, a], ignore_index=num_labels,
+                                      reduction="sum") / counts[a]
+            gl = gl + F.cross_entropy(gpn.transpose(1, 2), gt_nouns[sl, a], ignore_index=num_labels,
+                                      reduction="sum") / counts[a]
+        (vl + nl).backward()
+        vl, nl, gl = vl.detach(), nl.detach(), gl.detach()
+        tot += torch.tensor([vl.item(), nl.item(), gl.item()], dtype=torch.float64)
+        if keep_logits:
+            for dst, src in zip(logits, (pv, pn, gpn)):
+                dst.append(src.detach())
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in ps.items()}
+    outs = tuple(torch.cat(x) for x in logits) if keep_logits else None
+    return tuple(tot.to(torch.float32)), grads, outs

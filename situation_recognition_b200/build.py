@@ -41,7 +41,10 @@ def build(force=False, verbose=False):
             if f.read().strip() == digest:
                 return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    missing = [s for s in srcs if not os.path.exists(s)]
+    if missing:
+        raise RuntimeError("libsrggnn.so sources missing: %s" % ", ".join(missing))
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:

@@ -579,6 +579,7 @@ int srg_create(srg_handle** out, int device, int D, int R, int T, int n_verbs, i
 
 int srg_destroy(srg_handle* h) {
   if (!h) return SRG_OK;
+  DeviceGuard guard_(h->device);
   void* ptrs[] = {h->d_verb2roles, h->d_role_count, h->d_bad, h->Wzr, h->Wh, h->Wcn, h->Wcv, h->Wm_hi, h->Wm_mid, h->Wm_lo, h->Wp6,
                   h->P_hi, h->P_mid, h->P_lo, h->U_stack, h->Uh, h->wb, h->bzr[0], h->bzr[1], h->bh[0], h->bh[1], h->bcn, h->bcv,
                   h->acc_GP, h->acc_GPb, h->acc_s};
@@ -596,6 +597,8 @@ int srg_set_cta_group(srg_handle* h, int cta_group) {
 }
 
 int srg_set_tables(srg_handle* h, const int32_t* verb2roles, const int32_t* role_count) {
+  SRG_CHECK(h != nullptr, "srg_set_tables: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h && verb2roles && role_count, "srg_set_tables: null argument");
   for (int v = 0; v < h->V; ++v) {
     SRG_CHECK(role_count[v] >= 0 && role_count[v] <= h->R, "role_count[%d]=%d outside [0,%d]", v, role_count[v], h->R);
@@ -612,6 +615,8 @@ int srg_set_tables(srg_handle* h, const int32_t* verb2roles, const int32_t* role
 
 int srg_gather_mask(srg_handle* h, const int64_t* verb, int B, int64_t* role_idx, float* mask, int* bad_verb,
                     void* stream) {
+  SRG_CHECK(h != nullptr, "srg_gather_mask: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h != nullptr && h->tables_set, "srg_gather_mask: call srg_set_tables first");
   SRG_CHECK(B >= 0, "negative batch");
   if (B == 0) return SRG_OK;
@@ -621,6 +626,8 @@ int srg_gather_mask(srg_handle* h, const int64_t* verb, int B, int64_t* role_idx
 }
 
 int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_pack_weights: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h && p, "srg_pack_weights: null argument");
   SRG_CHECK(precision == SRG_PREC_BF16 || precision == SRG_PREC_FP32, "bad precision %d", precision);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -729,6 +736,8 @@ size_t srg_workspace_bytes(srg_handle* h, int mode, int B, int precision, int sa
 int srg_nouns_forward(srg_handle* h, const float* feat, const int64_t* verb, int B, const float* role_emb,
                       const float* verb_emb, const uint8_t* keep, float drop_p, float* logits, int64_t ldl,
                       int precision, int save_for_backward, void* workspace, size_t workspace_bytes, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_nouns_forward: null handle");
+  DeviceGuard guard_(h->device);
   PathBufs pb;
   SRG_TRY(check_ws(h, SRG_MODE_NOUN, B, precision, save_for_backward, workspace, workspace_bytes, &pb));
   SRG_CHECK(h->tables_set, "srg_nouns_forward: call srg_set_tables first");
@@ -745,6 +754,8 @@ int srg_nouns_forward(srg_handle* h, const float* feat, const int64_t* verb, int
 int srg_verb_forward(srg_handle* h, const float* feat, int B, const uint8_t* keep, float drop_p, float* logits,
                      int64_t ldl, int precision, int save_for_backward, void* workspace, size_t workspace_bytes,
                      void* stream) {
+  SRG_CHECK(h != nullptr, "srg_verb_forward: null handle");
+  DeviceGuard guard_(h->device);
   PathBufs pb;
   SRG_TRY(check_ws(h, SRG_MODE_VERB, B, precision, save_for_backward, workspace, workspace_bytes, &pb));
   SRG_CHECK(h->packed_prec == precision, "srg_verb_forward: weights are not packed for precision %d", precision);
@@ -757,6 +768,8 @@ int srg_verb_forward(srg_handle* h, const float* feat, int B, const uint8_t* kee
 
 int srg_ggnn_forward(srg_handle* h, int mode, float* hidden, const float* mask, int B, int precision,
                      int save_for_backward, void* workspace, size_t workspace_bytes, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_ggnn_forward: null handle");
+  DeviceGuard guard_(h->device);
   PathBufs pb;
   SRG_CHECK(mode == SRG_MODE_NOUN || mode == SRG_MODE_VERB, "bad mode %d", mode);
   SRG_TRY(check_ws(h, mode, B, precision, save_for_backward, workspace, workspace_bytes, &pb));
@@ -769,6 +782,8 @@ int srg_ggnn_forward(srg_handle* h, int mode, float* hidden, const float* mask, 
 }
 
 int srg_count_targets(srg_handle* h, const int64_t* gt_nouns, int B, float* counts, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_count_targets: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h && gt_nouns && counts, "srg_count_targets: null argument");
   return launch_count_targets(gt_nouns, B, h->R, h->L, counts, static_cast<cudaStream_t>(stream));
 }
@@ -776,6 +791,8 @@ int srg_count_targets(srg_handle* h, const int64_t* gt_nouns, int B, float* coun
 int srg_nouns_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_nouns, int B,
                    const float* counts, float* loss, float* dlogits, float grad_scale, const float* stats,
                    void* stream) {
+  SRG_CHECK(h != nullptr, "srg_nouns_loss: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h && logits && gt_nouns && counts && loss, "srg_nouns_loss: null argument");
   SRG_CHECK(ldl >= h->L, "srg_nouns_loss: ldl %lld < n_labels %d", (long long)ldl, h->L);
   return launch_nouns_ce(logits, ldl, h->L, gt_nouns, B, h->R, counts, loss, dlogits, grad_scale, nullptr, stats,
@@ -785,6 +802,8 @@ int srg_nouns_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_
 int srg_nouns_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_nouns, int B,
                             const float* counts, const float* grad_out, float grad_scale, float* dlogits,
                             const float* stats, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_nouns_loss_backward: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h && logits && gt_nouns && counts && dlogits, "srg_nouns_loss_backward: null argument");
   SRG_CHECK(ldl >= h->L, "srg_nouns_loss_backward: ldl %lld < n_labels %d", (long long)ldl, h->L);
   return launch_nouns_ce(logits, ldl, h->L, gt_nouns, B, h->R, counts, nullptr, dlogits, grad_scale, grad_out, stats,
@@ -792,20 +811,25 @@ int srg_nouns_loss_backward(srg_handle* h, const float* logits, int64_t ldl, con
 }
 
 int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B, float inv_batch,
-                  float* loss, float* dlogits, float grad_scale, const float* stats, void* stream) {
+                  const float* batch_total, float* loss, float* dlogits, float grad_scale, const float* stats,
+                  void* stream) {
+  SRG_CHECK(h != nullptr, "srg_verb_loss: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h && logits && gt_verb && loss, "srg_verb_loss: null argument");
   SRG_CHECK(ldl >= h->V, "srg_verb_loss: ldl %lld < n_verbs %d", (long long)ldl, h->V);
   return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, loss, dlogits, grad_scale, nullptr, stats,
-                        h->Vpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
+                        h->Vpad / ((h->cg == 2) ? 256 : 128), batch_total, static_cast<cudaStream_t>(stream));
 }
 
 int srg_verb_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B,
-                           float inv_batch, const float* grad_out, float grad_scale, float* dlogits,
-                           const float* stats, void* stream) {
+                           float inv_batch, const float* batch_total, const float* grad_out, float grad_scale,
+                           float* dlogits, const float* stats, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_verb_loss_backward: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h && logits && gt_verb && dlogits, "srg_verb_loss_backward: null argument");
   SRG_CHECK(ldl >= h->V, "srg_verb_loss_backward: ldl %lld < n_verbs %d", (long long)ldl, h->V);
   return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, nullptr, dlogits, grad_scale, grad_out, stats,
-                        h->Vpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
+                        h->Vpad / ((h->cg == 2) ? 256 : 128), batch_total, static_cast<cudaStream_t>(stream));
 }
 
 int srg_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
@@ -816,6 +840,8 @@ int srg_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf,
 }
 
 int srg_set_deferred_chain(srg_handle* h, int on, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_set_deferred_chain: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h != nullptr, "null handle");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t D = h->D;
@@ -833,6 +859,8 @@ int srg_set_deferred_chain(srg_handle* h, int on, void* stream) {
 }
 
 int srg_chain_finalize(srg_handle* h, const srg_grads* g, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_chain_finalize: null handle");
+  DeviceGuard guard_(h->device);
   SRG_CHECK(h != nullptr && g != nullptr, "srg_chain_finalize: null argument");
   SRG_CHECK(h->defer_chain && h->acc_GP != nullptr, "srg_chain_finalize: call srg_set_deferred_chain(h, 1) first");
   SRG_CHECK(h->packed_prec == SRG_PREC_BF16, "srg_chain_finalize needs bf16-packed weights");
@@ -847,6 +875,8 @@ int srg_chain_finalize(srg_handle* h, const srg_grads* g, void* stream) {
 int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const float* feat, const int64_t* verb, int B,
                        const float* role_emb, const float* verb_emb, const uint8_t* keep, float drop_p,
                        const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_nouns_backward: null handle");
+  DeviceGuard guard_(h->device);
   PathBufs pb;
   SRG_TRY(check_ws(h, SRG_MODE_NOUN, B, SRG_PREC_BF16, 1, workspace, workspace_bytes, &pb));
   SRG_CHECK(h->packed_prec == SRG_PREC_BF16, "backward needs bf16-packed weights");
@@ -855,13 +885,15 @@ int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const f
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SRG_TRY(path_backward(h, SRG_MODE_NOUN, pb, dlogits, ldl, B, keep, drop_p, g, s));
   if (g->role_emb != nullptr && g->verb_emb != nullptr)
-    SRG_TRY(launch_node_init_bwd(pb.dh, pb.hb_hi[0], feat, role_emb, verb_emb, verb, h->d_verb2roles, h->n_roles, B,
+    SRG_TRY(launch_node_init_bwd(pb.dh, pb.hb_hi[0], feat, role_emb, verb_emb, verb, h->d_verb2roles, h->V, h->n_roles, B,
                                  h->R, h->D, g->role_emb, g->verb_emb, s));
   return SRG_OK;
 }
 
 int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int B, const uint8_t* keep, float drop_p,
                       const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_verb_backward: null handle");
+  DeviceGuard guard_(h->device);
   PathBufs pb;
   SRG_TRY(check_ws(h, SRG_MODE_VERB, B, SRG_PREC_BF16, 1, workspace, workspace_bytes, &pb));
   SRG_CHECK(h->packed_prec == SRG_PREC_BF16, "backward needs bf16-packed weights");

@@ -55,7 +55,7 @@ int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_
                     const float* stats, int stats_tiles, cudaStream_t s);
 int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t* gt, int B, float inv_batch,
                    float* loss, float* dlogits, float grad_scale, const float* gscale_dev, const float* stats,
-                   int stats_tiles, cudaStream_t s);
+                   int stats_tiles, const float* batch_total, cudaStream_t s);
 // fp32 [rows, ld] (first n_valid columns) -> bf16 [rows, n_pad], zero padded
 int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, cudaStream_t s);
 
@@ -64,8 +64,8 @@ int launch_colsum(const bf16* X, int64_t ld, int rows, int n_cols, float* out1, 
                   float scale2, cudaStream_t s);
 // node-init backward (embedding gradients), model.py:132-144
 int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, const float* role_emb,
-                         const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_roles, int B,
-                         int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s);
+                         const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_verbs,
+                         int n_roles, int B, int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s);
 
 // adm[b,j,:] = add[b,j,:] + sum_i mask[b,i,j] * dm[b,i,:]   (bf16 in / bf16 out; mask == nullptr: identity, R = 1)
 int launch_aggregate_t_bf16(const bf16* dm, const float* mask, const bf16* add, int B, int R, int D, bf16* adm,

@@ -11,10 +11,12 @@ inline int launch_gemm_inst(const GemmProblem& p, const GemmMaps& maps, const Ge
                             cudaStream_t stream) {
   using Cfg = GemmCfg<CG, BLOCK_N, EPI, F32>;
   auto kern = gemm_kernel<CG, BLOCK_N, A_MN, B_MN, EPI, F32>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the attribute is per device (and per function): one flag per device this process has launched on
+  static bool attr_done[kMaxDevices] = {};
+  SRG_CHECK(dev.device >= 0 && dev.device < kMaxDevices, "device index %d out of range", dev.device);
+  if (!attr_done[dev.device]) {
     SRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
+    attr_done[dev.device] = true;
   }
   const int num_m_tiles = (p.M + kTileM * CG - 1) / (kTileM * CG);
   const int total_work = num_m_tiles * (p.N / BLOCK_N) * args.k_splits;

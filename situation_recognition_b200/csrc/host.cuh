@@ -48,6 +48,21 @@ enum : int {
     if (_rc != 0) return _rc;    \
   } while (0)
 
+// Entry points run on the device their handle was created on, whatever the caller's current device is.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev && dev >= 0) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+constexpr int kMaxDevices = 64;
+
 // ---------------------------------------------------------------- launch accounting / live kernel timing
 // g_launches counts every kernel this library launches (bench.py reports it as "gpu_launches").
 inline std::atomic<long long> g_launches{0};

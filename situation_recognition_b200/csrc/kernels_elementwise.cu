@@ -249,8 +249,12 @@ __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, i
                                 const int64_t* __restrict__ gt, int R, int ignore_index,
                                 const float* __restrict__ counts, float inv_fixed, float* __restrict__ loss,
                                 float* __restrict__ dlogits, float grad_scale, const float* __restrict__ gscale_dev,
-                                const float2* __restrict__ stats, int stats_tiles) {
+                                const float2* __restrict__ stats, int stats_tiles,
+                                const float* __restrict__ total_dev) {
   __shared__ float s_loss[kThreads / 32];
+  // total_dev: device scalar holding the GLOBAL number of rows the mean is taken over (all-reduced by the caller when
+  // the batch is sharded unevenly); overrides inv_fixed
+  if (total_dev != nullptr) inv_fixed = 1.0f / fmaxf(__ldg(total_dev), 1.0f);
   // gscale_dev: device scalar multiplied into the gradient (the incoming d(loss) of the autograd backward pass)
   if (gscale_dev != nullptr) grad_scale *= __ldg(gscale_dev);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -410,15 +414,16 @@ __global__ void k_colsum(const bf16* __restrict__ X, int64_t ld, int rows, int n
 __global__ void k_node_init_bwd(const float* __restrict__ dh0, const bf16* __restrict__ h0b,
                                 const float* __restrict__ feat, const float* __restrict__ role_emb,
                                 const float* __restrict__ verb_emb, const int64_t* __restrict__ verb,
-                                const int32_t* __restrict__ verb2roles, int n_roles, int B, int R, int D,
-                                float* __restrict__ d_role_emb, float* __restrict__ d_verb_emb) {
+                                const int32_t* __restrict__ verb2roles, int n_verbs, int n_roles, int B, int R,
+                                int D, float* __restrict__ d_role_emb, float* __restrict__ d_verb_emb) {
   const int D4 = D / 4;
   const int64_t total = static_cast<int64_t>(B) * D4;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int b = static_cast<int>(t / D4);
     const int d = static_cast<int>(t % D4) * 4;
-    const int64_t v = verb[b];
+    int64_t v = verb[b];
+    if (v < 0 || v >= n_verbs) v = 0;   // same clamp as the forward kernels (which also raise the bad-verb flag)
     const float4 f = *reinterpret_cast<const float4*>(feat + static_cast<int64_t>(b) * D + d);
     const float4 ve = *reinterpret_cast<const float4*>(verb_emb + v * D + d);
     float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -805,21 +810,21 @@ int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_
   if (stats_tiles > 32) stats = nullptr;
   k_cross_entropy<3><<<blocks, kThreads, 0, s>>>(logits, ldl, n_labels, rows, gt, R, n_labels, counts, 0.f, loss,
                                                 dlogits, grad_scale, gscale_dev,
-                                                reinterpret_cast<const float2*>(stats), stats_tiles);
+                                                reinterpret_cast<const float2*>(stats), stats_tiles, nullptr);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
 int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t* gt, int B, float inv_batch,
                    float* loss, float* dlogits, float grad_scale, const float* gscale_dev, const float* stats,
-                   int stats_tiles, cudaStream_t s) {
+                   int stats_tiles, const float* batch_total, cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   int blocks = (B + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (stats_tiles > 32) stats = nullptr;
   k_cross_entropy<1><<<blocks, kThreads, 0, s>>>(logits, ldl, n_verbs, B, gt, 1, -100, nullptr, inv_batch, loss,
                                                 dlogits, grad_scale, gscale_dev,
-                                                reinterpret_cast<const float2*>(stats), stats_tiles);
+                                                reinterpret_cast<const float2*>(stats), stats_tiles, batch_total);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
@@ -844,11 +849,11 @@ int launch_colsum(const bf16* X, int64_t ld, int rows, int n_cols, float* out1, 
 }
 
 int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, const float* role_emb,
-                         const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_roles, int B,
-                         int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s) {
+                         const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_verbs,
+                         int n_roles, int B, int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   k_node_init_bwd<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(
-      dh0, h0b, feat, role_emb, verb_emb, verb, verb2roles, n_roles, B, R, D, d_role_emb, d_verb_emb);
+      dh0, h0b, feat, role_emb, verb_emb, verb, verb2roles, n_verbs, n_roles, B, R, D, d_role_emb, d_verb_emb);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }

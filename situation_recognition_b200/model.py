@@ -79,6 +79,8 @@ class _Engine:
         _lib.check(self.lib.srg_set_tables(self.h, v2r.ctypes.data_as(ctypes.c_void_p),
                                            rc.ctypes.data_as(ctypes.c_void_p)))
         self._packed_key = None
+        self.pack_gen = 0          # bumped whenever the packed operands are rebuilt (a backward pass must see the
+                                   # operands its forward pass ran with)
         self.launches = 0
         self._deferred = False     # srg_set_deferred_chain state of the handle
         self._pending = None       # direct-gradient backward pass in flight: {"grads", "events"}
@@ -113,8 +115,15 @@ class _Engine:
             if p.dtype != torch.float32 or not p.is_contiguous() or p.device != self.device:
                 raise _lib.SrgError("GGNN parameters must be contiguous fp32 tensors on %s" % self.device)
         sp = _lib.SrgParams(*[ctypes.c_void_p(p.data_ptr()) for p in params])
-        _lib.check(self.lib.srg_pack_weights(self.h, ctypes.byref(sp), prec, _lib.stream_ptr()))
+        _lib.check(self.lib.srg_pack_weights(self.h, ctypes.byref(sp), prec, self.stream()))
         self._packed_key = key
+        self.pack_gen += 1
+
+    def check_pack_gen(self, gen):
+        if gen != self.pack_gen:
+            raise _lib.SrgError("the packed weights changed between this path's forward and its backward pass (another "
+                                "forward after a parameter update, or a different precision): gradients would be "
+                                "inconsistent -- run backward() before the next forward / optimizer step")
 
     # ---- direct-gradient backward passes (flat buffers): one chain rule for all paths, one join of the side streams
     def set_deferred(self, on):
@@ -123,9 +132,9 @@ class _Engine:
         if self._pending is not None:
             self.finish_backward()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.srg_set_deferred_chain(self.h, int(on), _lib.stream_ptr()))
+            _lib.check(self.lib.srg_set_deferred_chain(self.h, int(on), self.stream()))
             if on:
-                torch.cuda.current_stream().synchronize()   # one-off: the cleared accumulators are visible to all streams
+                torch.cuda.current_stream(self.device).synchronize()   # one-off: the cleared accumulators are visible to all streams
         self._deferred = on
 
     def backward_begin(self, grads):
@@ -155,11 +164,15 @@ class _Engine:
         if pend is None:
             return
         with torch.cuda.device(self.device):
-            cur = torch.cuda.current_stream()
+            cur = torch.cuda.current_stream(self.device)
             for ev in pend["events"]:
                 cur.wait_event(ev)
             sg = _grad_struct(pend["grads"], self)
-            _lib.check(self.lib.srg_chain_finalize(self.h, ctypes.byref(sg), _lib.stream_ptr()))
+            _lib.check(self.lib.srg_chain_finalize(self.h, ctypes.byref(sg), self.stream()))
+
+    def stream(self):
+        """Current stream of THIS engine's device (the caller's current device may be another GPU)."""
+        return _lib.stream_ptr(self.device)
 
     def workspace(self, mode, B, prec, save):
         n = self.lib.srg_workspace_bytes(self.h, mode, B, prec, int(save))
@@ -219,9 +232,10 @@ class _NounsStage(torch.autograd.Function):
         verb = verb.detach().to(torch.int64).contiguous()
         _lib.check(eng.lib.srg_nouns_forward(eng.h, _lib.ptr(feat), _lib.ptr(verb), B, _lib.ptr(role_emb),
                                              _lib.ptr(verb_emb), _lib.ptr(keep), drop_p, _lib.ptr(logits), eng.Lpad,
-                                             prec, int(need_grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+                                             prec, int(need_grad), _lib.ptr(ws), ws.numel(), eng.stream()))
         if need_grad:
             ctx.eng, ctx.ws, ctx.B, ctx.drop_p = eng, ws, B, drop_p
+            ctx.pack_gen = eng.pack_gen
             ctx.direct = model._direct_grads()
             ctx.live = (role_emb, verb_emb) + tuple(params)       # the Parameter objects (for .grad in direct mode)
             ctx.save_for_backward(feat, verb, keep, role_emb, verb_emb, *params)
@@ -231,6 +245,7 @@ class _NounsStage(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         eng = ctx.eng
+        eng.check_pack_gen(ctx.pack_gen)
         feat, verb, keep, role_emb, verb_emb, *params = ctx.saved_tensors
         B = ctx.B
         dl, ldl = _padded_grad(dlogits.reshape(B * eng.R, eng.L), eng.Lpad)
@@ -244,7 +259,7 @@ class _NounsStage(torch.autograd.Function):
         sg = _grad_struct(grads, eng)
         _lib.check(eng.lib.srg_nouns_backward(eng.h, _lib.ptr(dl), ldl, _lib.ptr(feat), _lib.ptr(verb), B,
                                               _lib.ptr(role_emb), _lib.ptr(verb_emb), _lib.ptr(keep), ctx.drop_p,
-                                              ctypes.byref(sg), _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()))
+                                              ctypes.byref(sg), _lib.ptr(ctx.ws), ctx.ws.numel(), eng.stream()))
         ctx.ws = None
         if ctx.direct:
             eng.backward_mark()
@@ -270,9 +285,10 @@ class _VerbStage(torch.autograd.Function):
         ws = eng.workspace(SRG_MODE_VERB, B, prec, need_grad)
         _lib.check(eng.lib.srg_verb_forward(eng.h, _lib.ptr(feat), B, _lib.ptr(keep), drop_p, _lib.ptr(logits),
                                             eng.Vpad, prec, int(need_grad), _lib.ptr(ws), ws.numel(),
-                                            _lib.stream_ptr()))
+                                            eng.stream()))
         if need_grad:
             ctx.eng, ctx.ws, ctx.B, ctx.drop_p = eng, ws, B, drop_p
+            ctx.pack_gen = eng.pack_gen
             ctx.direct = model._direct_grads()
             ctx.live = tuple(params)
             ctx.save_for_backward(keep, *params)
@@ -282,6 +298,7 @@ class _VerbStage(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         eng = ctx.eng
+        eng.check_pack_gen(ctx.pack_gen)
         keep, *params = ctx.saved_tensors
         B = ctx.B
         dl, ldl = _padded_grad(dlogits.reshape(B, eng.V), eng.Vpad)
@@ -294,7 +311,7 @@ class _VerbStage(torch.autograd.Function):
             eng.set_deferred(False)
         sg = _grad_struct(grads, eng)
         _lib.check(eng.lib.srg_verb_backward(eng.h, _lib.ptr(dl), ldl, B, _lib.ptr(keep), ctx.drop_p, ctypes.byref(sg),
-                                             _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()))
+                                             _lib.ptr(ctx.ws), ctx.ws.numel(), eng.stream()))
         ctx.ws = None
         if ctx.direct:
             eng.backward_mark()
@@ -353,14 +370,14 @@ class _NounsLoss(torch.autograd.Function):
             counts = cached[1]
         else:
             counts = torch.empty(3, dtype=torch.float32, device=logits.device)
-            _lib.check(eng.lib.srg_count_targets(eng.h, _lib.ptr(gt), B, _lib.ptr(counts), _lib.stream_ptr()))
+            _lib.check(eng.lib.srg_count_targets(eng.h, _lib.ptr(gt), B, _lib.ptr(counts), eng.stream()))
             if model.loss_group is not None:
                 torch.distributed.all_reduce(counts, group=model.loss_group)
             model._counts_cache = (key, counts, gt)     # holding gt keeps its address from being reused
         loss = torch.zeros((), dtype=torch.float32, device=logits.device)
         _lib.check(eng.lib.srg_nouns_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts), _lib.ptr(loss),
                                           None, 1.0, ctypes.c_void_p(stats[1]) if stats else None,
-                                          _lib.stream_ptr()))
+                                          eng.stream()))
         if grad_on and ctx.needs_input_grad[2]:
             ctx.save_for_backward(x, gt, counts)
             ctx.eng, ctx.geom, ctx.shape, ctx.stats = eng, (rows, ld, B), tuple(logits.shape), stats
@@ -374,7 +391,7 @@ class _NounsLoss(torch.autograd.Function):
         dl = torch.empty(rows, ld, dtype=torch.float32, device=x.device)
         _lib.check(eng.lib.srg_nouns_loss_backward(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts),
                                                    _lib.ptr(gout), 1.0, _lib.ptr(dl),
-                                                   ctypes.c_void_p(stats[1]) if stats else None, _lib.stream_ptr()))
+                                                   ctypes.c_void_p(stats[1]) if stats else None, eng.stream()))
         ctx.stats = None
         return None, None, dl[:, :eng.L].view(ctx.shape), None, None
 
@@ -389,27 +406,36 @@ class _VerbLoss(torch.autograd.Function):
         if x.data_ptr() != logits.data_ptr():
             stats = None
         gt = gt_verb.detach().to(torch.int64).contiguous()
-        world = 1
-        if model.loss_group is not None:
-            world = torch.distributed.get_world_size(model.loss_group)
         loss = torch.zeros((), dtype=torch.float32, device=logits.device)
-        inv = 1.0 / (rows * world)
-        _lib.check(eng.lib.srg_verb_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, inv, _lib.ptr(loss), None, 1.0,
-                                         ctypes.c_void_p(stats[1]) if stats else None, _lib.stream_ptr()))
+        # The mean is over the GLOBAL batch (the reference computes the loss on the gathered logits of all replicas,
+        # sr.py:66-68).  Shards may be unequal (tail batch of an epoch), so rows * world is NOT the denominator: the
+        # caller states the global batch (model.global_batch), or the local batch sizes are all-reduced on the stream.
+        inv, total = 1.0 / rows, None
+        if model.loss_group is not None:
+            if model.global_batch is not None:
+                inv = 1.0 / float(model.global_batch)
+            else:
+                total = torch.full((1,), float(rows), dtype=torch.float32, device=logits.device)
+                torch.distributed.all_reduce(total, group=model.loss_group)
+        _lib.check(eng.lib.srg_verb_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, inv, _lib.ptr(total),
+                                         _lib.ptr(loss), None, 1.0, ctypes.c_void_p(stats[1]) if stats else None,
+                                         eng.stream()))
         if grad_on and ctx.needs_input_grad[2]:
-            ctx.save_for_backward(x, gt)
+            saved = (x, gt) if total is None else (x, gt, total)
+            ctx.save_for_backward(*saved)
             ctx.eng, ctx.geom, ctx.shape, ctx.stats = eng, (rows, ld, inv), tuple(logits.shape), stats
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        x, gt = ctx.saved_tensors
+        x, gt, *rest = ctx.saved_tensors
+        total = rest[0] if rest else None
         eng, (rows, ld, inv), stats = ctx.eng, ctx.geom, ctx.stats
         gout = gout.detach().to(torch.float32).contiguous()
         dl = torch.empty(rows, ld, dtype=torch.float32, device=x.device)
-        _lib.check(eng.lib.srg_verb_loss_backward(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, inv, _lib.ptr(gout), 1.0,
-                                                  _lib.ptr(dl), ctypes.c_void_p(stats[1]) if stats else None,
-                                                  _lib.stream_ptr()))
+        _lib.check(eng.lib.srg_verb_loss_backward(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, inv, _lib.ptr(total),
+                                                  _lib.ptr(gout), 1.0, _lib.ptr(dl),
+                                                  ctypes.c_void_p(stats[1]) if stats else None, eng.stream()))
         ctx.stats = None
         return None, None, dl[:, :eng.V].view(ctx.shape), None, None
 
@@ -450,6 +476,8 @@ class FCGGNN(nn.Module):
         self.precision = precision
         self.drop_p = 0.5
         self.loss_group = None          # torch.distributed group over which loss denominators are global
+        self.global_batch = None        # images of the current GLOBAL batch when the caller knows it (saves the
+                                        # all-reduce of the local batch sizes in verb_loss); None = all-reduce
         self.dropout_masks = None       # optional (verb, pred-noun, gt-noun) uint8 keep-masks for parity tests
         self.role_emb = nn.Embedding(encoder.get_num_roles() + 1, D_hidden_state, padding_idx=encoder.get_num_roles())
         self.verb_emb = nn.Embedding(encoder.get_num_verbs(), D_hidden_state)
@@ -600,7 +628,7 @@ class FCGGNN(nn.Module):
             mk = mask.detach().to(device=h.device, dtype=torch.float32).contiguous()
         ws = eng.workspace(mode, B, prec, False)
         _lib.check(eng.lib.srg_ggnn_forward(eng.h, mode, _lib.ptr(h), _lib.ptr(mk), B, prec, 0, _lib.ptr(ws),
-                                            ws.numel(), _lib.stream_ptr()))
+                                            ws.numel(), eng.stream()))
         return h
 
     def gather_mask(self, verbs):
@@ -615,5 +643,5 @@ class FCGGNN(nn.Module):
         mask = torch.empty(B, R, R, dtype=torch.float32, device=v.device)
         bad = torch.zeros(1, dtype=torch.int32, device=v.device)
         _lib.check(eng.lib.srg_gather_mask(eng.h, _lib.ptr(v), B, _lib.ptr(role_idx), _lib.ptr(mask), _lib.ptr(bad),
-                                           _lib.stream_ptr()))
+                                           eng.stream()))
         return role_idx, mask, bad

@@ -32,6 +32,28 @@ def agree(a, b):
     return (a.detach().argmax(-1).cpu() == b.detach().argmax(-1).cpu()).float().mean().item()
 
 
+def report(name, **values):
+    """Print the measured errors (visible with `pytest -rA` / on failure) and append them to gpurun_out/parity_report.jsonl
+    so the numbers of a GPU run can be committed under profiles/."""
+    line = {"test": name, **values}
+    print("PARITY " + json.dumps(line))
+    try:
+        out = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(line) + "\n")
+    except OSError:
+        pass
+
+
+def grad_errors(model, ref_grads):
+    errs = {}
+    for k, p in model.named_parameters():
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        errs[k] = relmax(got, ref_grads[k])
+    return errs
+
+
 @pytest.fixture(scope="module")
 def enc_syn():
     return S.imsitu_encoder(make_train_json(seed=0), verbose=False)
@@ -217,16 +239,24 @@ def test_images_are_independent_and_batch_one(enc_syn, cfg2):
     assert torch.equal(one[0], full[3]) and torch.equal(seven, full[100:107]) and torch.equal(vone[0], vfull[9])
 
 
-@pytest.mark.parametrize("flat", [False, True])
-def test_train_step_gradients_vs_oracle(enc_syn, flat):
-    B, D = 48, 2048
+def _keep_masks(B, D, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(B, D, generator=g) < 0.5, torch.rand(B * 6, D, generator=g) < 0.5,
+            torch.rand(B * 6, D, generator=g) < 0.5)
+
+
+@pytest.mark.parametrize("B,flat", [(48, False), (48, True), (768, True)])
+def test_train_step_gradients_vs_oracle(enc_syn, B, flat):
+    """One training step (sr.py:63-79) at D = 2048 with explicit dropout masks against the oracle: logits of all three
+    paths, the three losses and the gradients of all 20 tensors.  The oracle's predicted-verb noun path is conditioned
+    on the CUDA path's OWN predicted verbs (bf16 flips ~1 % of the nearly tied random-init argmaxes), so every
+    comparison runs unconditionally.  B = 768 is the per-GPU shard of the 8-GPU benchmark (M = 4608 node rows:
+    18 row tiles x 8-16 column tiles per launch, i.e. the multi-tile persistent schedule of every fused epilogue)."""
+    D = 2048
     params = O.init_params(504, 190, 2001, D, seed=0)
     fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=77)
     t, c = O.build_tables(enc_syn.roles_per_verb, enc_syn.verb_list, enc_syn.role_list)
-    g = torch.Generator().manual_seed(5)
-    keeps = (torch.rand(B, D, generator=g) < 0.5, torch.rand(B * 6, D, generator=g) < 0.5,
-             torch.rand(B * 6, D, generator=g) < 0.5)
-    (vl, nl, gl), grads, (pv, pn, gpn) = O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, 2001, keeps, 0.5)
+    keeps = _keep_masks(B, D)
     m = model_from(params, enc_syn, D, "bf16").train()
     m.dropout_masks = tuple(k.to(torch.uint8).cuda() for k in keeps)
     if flat:     # direct accumulation into the flat buffer, deferred chain rule, side-stream join at the end of backward
@@ -235,19 +265,107 @@ def test_train_step_gradients_vs_oracle(enc_syn, flat):
     mpv, mpn, mgpn = m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())
     lv, ln, lg = m.verb_loss(mpv, gt_verb.cuda()), m.nouns_loss(mpn, gt_nouns.cuda()), m.nouns_loss(mgpn, gt_nouns.cuda())
     (lv + ln).backward()
-    if flat:     # a second pass accumulates: twice the gradient (the handle-level accumulators were cleared in between)
+    pred = mpv.argmax(-1).cpu()
+    if B <= 256:
+        (vl, nl, gl), grads, (pv, pn, gpn) = O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, 2001, keeps, 0.5,
+                                                                pred_verbs=pred)
+    else:
+        (vl, nl, gl), grads, (pv, pn, gpn) = O.train_step_grads_chunked(params, fv, fn, gt_verb, gt_nouns, t, c, 2001,
+                                                                        keeps, 0.5, pred_verbs=pred, keep_logits=True)
+    if flat and B <= 256:   # a second pass accumulates: twice the gradient (the handle-level accumulators were cleared)
         first = {k: p.grad.clone() for k, p in m.named_parameters()}
         mpv2, mpn2, _ = m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())
         (m.verb_loss(mpv2, gt_verb.cuda()) + m.nouns_loss(mpn2, gt_nouns.cuda())).backward()
         for k, p in m.named_parameters():
             assert relmax(p.grad, 2 * first[k]) <= 1e-3, k
             p.grad.copy_(first[k])
+    errs = grad_errors(m, grads)
+    report("train_step_gradients_vs_oracle[B=%d,flat=%s]" % (B, flat), verb_flips=int((pred != pv.argmax(-1)).sum()),
+           logits={"verb": relmax(mpv, pv), "pred_nouns": relmax(mpn, pn), "gt_nouns": relmax(mgpn, gpn)},
+           losses={"cuda": [lv.item(), ln.item(), lg.item()], "oracle": [float(vl), float(nl), float(gl)]}, grads=errs)
     assert relmax(mgpn, gpn) <= BF16_TOL and relmax(mpv, pv) <= BF16_TOL       # dropout-mask parity included
-    assert abs(lv.item() - float(vl)) <= 2e-3 * float(vl) and abs(lg.item() - float(gl)) <= 2e-3 * float(gl)
-    if torch.equal(mpv.argmax(-1).cpu(), pv.argmax(-1)):       # same predicted verbs => same pred-noun graph
-        assert abs(ln.item() - float(nl)) <= 2e-3 * float(nl)
-        for k, p in m.named_parameters():
-            assert relmax(p.grad, grads[k]) <= 3e-2, k
+    assert relmax(mpn, pn) <= BF16_TOL                                         # same role graphs by construction
+    for mine, ref in ((lv, vl), (ln, nl), (lg, gl)):
+        assert abs(mine.item() - float(ref)) <= 2e-3 * float(ref)
+    for k, e in errs.items():
+        assert e <= 3e-2, (k, e)
+
+
+def test_full_batch_gradients_vs_oracle(enc_syn):
+    """BASELINE.json configs[2] as benchmarked: B = 6144, D = 2048, train mode (explicit dropout masks), flat gradient /
+    parameter buffers (what bench.py runs).  The oracle processes the batch in 256-image chunks with the global loss
+    denominators and sums the gradients (oracle.train_step_grads_chunked) -- about a minute of CPU."""
+    from situation_recognition_b200 import parallel
+    B, D = 6144, 2048
+    params = O.init_params(504, 190, 2001, D, seed=0)
+    fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=1234)
+    t, c = O.build_tables(enc_syn.roles_per_verb, enc_syn.verb_list, enc_syn.role_list)
+    keeps = _keep_masks(B, D, seed=6)
+    m = model_from(params, enc_syn, D, "bf16").train()
+    m.dropout_masks = tuple(k.to(torch.uint8).cuda() for k in keeps)
+    flat = parallel.attach(m, flat_params=True)
+    flat.zero()
+    mpv, mpn, mgpn = m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())
+    lv, ln, lg = m.verb_loss(mpv, gt_verb.cuda()), m.nouns_loss(mpn, gt_nouns.cuda()), m.nouns_loss(mgpn, gt_nouns.cuda())
+    (lv + ln).backward()
+    torch.cuda.synchronize()
+    pred = mpv.argmax(-1).cpu()
+    (vl, nl, gl), grads, _ = O.train_step_grads_chunked(params, fv, fn, gt_verb, gt_nouns, t, c, 2001, keeps, 0.5,
+                                                        pred_verbs=pred, chunk=256)
+    errs = grad_errors(m, grads)
+    report("full_batch_gradients_vs_oracle[B=6144]",
+           losses={"cuda": [lv.item(), ln.item(), lg.item()], "oracle": [float(vl), float(nl), float(gl)]}, grads=errs)
+    for mine, ref in ((lv, vl), (ln, nl), (lg, gl)):
+        assert abs(mine.item() - float(ref)) <= 2e-3 * float(ref)
+    for k, e in errs.items():
+        assert e <= 3e-2, (k, e)
+    assert float(m.role_emb.weight.grad[enc_syn.get_num_roles()].abs().max()) == 0.0
+
+
+def test_argmax_agreement_with_real_margins(enc_syn):
+    """north_star: top-1 verb and label argmax identical on >= 99.9 % of samples.  With random-init weights the logits
+    are nearly tied (top-1/top-2 gap ~1e-2 of the range) and the criterion only measures rounding noise, so here the
+    model is first FITTED: 30 steps of the bf16 CUDA training path (dropout on, fused clip + Adamax) on one batch whose
+    three annotations agree, which separates the logits (verb margin ~8, label margin ~5 on a range of ~15 in the same
+    experiment on the CPU oracle).  Then the bf16 CUDA forward is compared with the fp32 oracle ON THE FITTED WEIGHTS.
+    Asserted on the verb rows and on the scored label rows (r < n_roles(gt verb): the rows imsitu_scorer reads)."""
+    from situation_recognition_b200 import parallel
+    B, D = 256, 2048
+    params = O.init_params(504, 190, 2001, D, seed=0)
+    fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=11)
+    gt_nouns = gt_nouns[:, :1].expand(-1, 3, -1).contiguous()
+    t, c = O.build_tables(enc_syn.roles_per_verb, enc_syn.verb_list, enc_syn.role_list)
+    m = model_from(params, enc_syn, D, "bf16").train()
+    flat = parallel.attach(m, flat_params=True)
+    opt = parallel.FlatAdamax(flat, lr=0.002, max_norm=1.0)
+    dfv, dfn, dgv, dgn = fv.cuda(), fn.cuda(), gt_verb.cuda(), gt_nouns.cuda()
+    losses = []
+    for _ in range(30):
+        flat.zero()
+        pv, pn, _ = m(dfv, dgv, img_nouns=dfn)
+        loss = m.verb_loss(pv, dgv) + m.nouns_loss(pn, dgn)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < 0.2 * losses[0], losses
+    m.eval()
+    with torch.no_grad():
+        mpv, mpn, mgpn = m(dfv, dgv, img_nouns=dfn)
+    fitted = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        pv, pn, gpn = O.forward(fitted, fv, fn, gt_verb, t, c, pred_verbs=mpv.argmax(-1).cpu())
+    counts = torch.tensor([enc_syn.get_role_count(int(v)) for v in gt_verb])
+    scored = torch.arange(6)[None, :] < counts[:, None]
+    top2 = pv.topk(2, -1).values
+    top2n = gpn[scored].topk(2, -1).values
+    res = {"verb": agree(mpv, pv), "gt_nouns_scored": agree(mgpn.cpu()[scored], gpn[scored]),
+           "pred_nouns_scored": agree(mpn.cpu()[scored], pn[scored]), "gt_nouns_all_rows": agree(mgpn, gpn),
+           "verb_margin_median": float((top2[:, 0] - top2[:, 1]).median()),
+           "noun_margin_median": float((top2n[:, 0] - top2n[:, 1]).median()),
+           "logit_err": {"verb": relmax(mpv, pv), "gt_nouns": relmax(mgpn, gpn)}, "loss_first_last": [losses[0], losses[-1]]}
+    report("argmax_agreement_with_real_margins", **res)
+    assert res["verb"] >= 0.999 and res["gt_nouns_scored"] >= 0.999 and res["pred_nouns_scored"] >= 0.999, res
+    assert relmax(mpv, pv) <= BF16_TOL and relmax(mgpn, gpn) <= BF16_TOL
 
 
 def test_fp32_mode_is_forward_only(enc_syn):
@@ -279,7 +397,8 @@ def test_full_size_step_properties(enc_syn):
 
 
 def test_graphed_step_matches_eager(enc_syn):
-    """The CUDA-graph replay of a training step produces the same losses and parameter updates as eager launches."""
+    """The CUDA-graph replay of a training step (as bench.py --graph / the multi-GPU default runs it: flat buffers,
+    fused clip + Adamax) produces the same losses AND the same parameter updates as eager launches."""
     from situation_recognition_b200 import parallel
     from situation_recognition_b200.graph import GraphedTrainStep
     B, D = 24, 2048
@@ -291,15 +410,16 @@ def test_graphed_step_matches_eager(enc_syn):
     for graphed in (False, True):
         m = model_from(params, enc_syn, D, "bf16").train()
         m.dropout_masks = keeps
-        flat = parallel.attach(m)
-        opt = torch.optim.Adamax(m.parameters(), lr=0.002, capturable=True)
-        gs = GraphedTrainStep(m, opt, flat, B, warmup=0 if not graphed else 2)
+        flat = parallel.attach(m, flat_params=True)
+        opt = parallel.FlatAdamax(flat, lr=0.002, max_norm=1.0)
+        gs = GraphedTrainStep(m, opt, flat, B, warmup=2)
         if graphed:
             snap = {k: v.detach().clone() for k, v in m.state_dict().items()}
-            gs.capture(batch)                       # warm-up steps move the weights: restore them, reset Adamax
-            m.load_state_dict(snap)
-            opt.state.clear()
-            opt2 = None
+            gs.capture(batch)                       # the warm-up steps moved the weights and the optimizer state:
+            m.load_state_dict(snap)                 # restore both IN PLACE (the graph holds their addresses)
+            opt.exp_avg.zero_()
+            opt.exp_inf.zero_()
+            opt.scratch.zero_()
             losses = [gs(*batch).clone() for _ in range(2)]
         else:
             for dst, src in zip(gs.static_in, batch):
@@ -309,6 +429,18 @@ def test_graphed_step_matches_eager(enc_syn):
         results.append((torch.stack(losses).cpu(), {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}))
     (l0, p0), (l1, p1) = results
     assert torch.allclose(l0[0], l1[0], rtol=1e-5, atol=1e-6)          # first step: identical weights and masks
+    # second step and the parameters after it: split-K reduce-adds and atomics make the gradient sums order dependent in
+    # the last bits; the two runs must agree far below the size of an update (lr = 2e-3 per step)
+    assert torch.allclose(l0[1], l1[1], rtol=1e-3, atol=1e-4)
+    # (the first Adamax step moves every weight by lr * sign(g): an element whose gradient is within that rounding noise
+    # of zero may legitimately go the other way, so a vanishing fraction of outliers is tolerated, bounded by 2 updates)
+    moved = 0.0
+    for k in p0:
+        diff = (p0[k] - p1[k]).abs()
+        assert (diff > 1e-4).float().mean().item() <= 1e-4 and diff.max().item() <= 2 * 2 * 2e-3 + 1e-4, \
+            (k, diff.max().item(), (diff > 1e-4).float().mean().item())
+        moved = max(moved, (p0[k] - params[k]).abs().max().item())
+    assert moved > 2e-3                                                # two steps did update the weights
 
 
 def test_fused_clip_adamax_matches_torch(enc_syn):
@@ -368,19 +500,19 @@ def test_ragged_batches_train_step(enc_syn, B):
     params = O.init_params(504, 190, 2001, D, seed=1)
     fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=B)
     t, c = O.build_tables(enc_syn.roles_per_verb, enc_syn.verb_list, enc_syn.role_list)
-    (vl, nl, gl), grads, (pv, pn, gpn) = O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, 2001)
     m = model_from(params, enc_syn, D, "bf16").eval()
     mpv, mpn, mgpn = m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())
     assert mpn.shape == (B, 6, 2001)
     lv, ln = m.verb_loss(mpv, gt_verb.cuda()), m.nouns_loss(mpn, gt_nouns.cuda())
     (lv + ln).backward()
-    assert relmax(mgpn, gpn) <= BF16_TOL and relmax(mpv, pv) <= BF16_TOL
-    assert abs(lv.item() - float(vl)) <= 5e-3 * float(vl)
+    (vl, nl, gl), grads, (pv, pn, gpn) = O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, 2001,
+                                                            pred_verbs=mpv.argmax(-1).cpu())
+    assert relmax(mgpn, gpn) <= BF16_TOL and relmax(mpv, pv) <= BF16_TOL and relmax(mpn, pn) <= BF16_TOL
+    assert abs(lv.item() - float(vl)) <= 5e-3 * float(vl) and abs(ln.item() - float(nl)) <= 5e-3 * float(nl)
     for k, p in m.named_parameters():
         assert torch.isfinite(p.grad).all(), k
-    if torch.equal(mpv.argmax(-1).cpu(), pv.argmax(-1)):
-        for k, p in m.named_parameters():
-            assert relmax(p.grad, grads[k]) <= 3e-2, k
+    for k, e in grad_errors(m, grads).items():
+        assert e <= 3e-2, (k, e)
 
 
 def test_loss_backward_scales_with_incoming_gradient(enc_syn):

@@ -40,7 +40,9 @@ CASES = [
 ]
 
 
-def run_case(idx):
+def check_case(idx, time_it=True):
+    """Run CASES[idx] on the current CUDA device and return {"case", "max_abs_err", "ref_max", "ok"[, "ms", "tflops"]}.
+    tests/test_gemm_cases.py runs every case through this in the -m gpu suite."""
     import torch
     name, cg, a_mn, b_mn, c_dt, M, N, K, use_bias, alpha, k_splits, reduce = CASES[idx]
     lib = ctypes.CDLL(LIB)
@@ -78,6 +80,8 @@ def run_case(idx):
     scale = ref.abs().max().item()
     tol = (2e-2 if c_dt == 2 else 2e-3) * max(scale, 1.0)
     out = {"case": name, "max_abs_err": err, "ref_max": scale, "ok": bool(err <= tol)}
+    if not time_it:
+        return out
     if M * N * K >= 10 ** 10 and not reduce:
         for _ in range(3):
             call()
@@ -102,6 +106,11 @@ def run_case(idx):
         ms = e0.elapsed_time(e1) / 5
         out["ms"] = ms
         out["tflops"] = 2.0 * M * N * K / ms / 1e9
+    return out
+
+
+def run_case(idx):
+    out = check_case(idx)
     print("RESULT " + json.dumps(out), flush=True)
     return 0 if out["ok"] else 1
 
