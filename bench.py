@@ -131,26 +131,33 @@ def reference_runner(sample):
 
 
 def cpu_baseline(steps=8):
-    """The reference's CPU implementation of the step, timed on this host's cores on a bounded sample (~10-30 s)."""
-    import torch
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
-    run, kind, what = reference_runner(REF_SAMPLE)
-    run()
-    t0 = time.time()
-    n = 0
-    while n < steps and (n < 2 or time.time() - t0 < 25.0):
-        run()
-        n += 1
-    dt = (time.time() - t0) / n
-    return {"value": REF_SAMPLE / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
-            "sample": "%d steps of %d images each (of the 6144-image step) after 1 warm-up: %s; os.cpu_count()=%s"
-                      % (n, REF_SAMPLE, what, os.cpu_count())}
+    """The reference's CPU implementation of the step, timed on this host's cores on a bounded sample (~10-30 s).
+
+    Runs `bench.py --impl reference` in a child process with the GPU hidden: the unmodified reference moves its index
+    tensors to CUDA whenever `torch.cuda.is_available()` (model.py:118-119,148-149), so its CPU path only runs in a
+    process that sees no GPU."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS"):
+        env.pop(k, None)
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps),
+                              "--warmup", "1"], env=env, capture_output=True, text=True, timeout=600)
+        lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+        cb = json.loads(lines[-1])["cpu_baseline"]
+        cb["sample"] = "%d steps after 1 warm-up; %s" % (steps, cb["sample"])
+        return cb
+    except Exception as e:   # the GPU measurement above must not be lost to a CPU-leg failure
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
+                "sample": "cpu leg failed: %s" % (str(e)[:200],)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # The unmodified reference sends its role-index / mask tensors to CUDA whenever a GPU is visible
+    # (model.py:118-119,148-149): its CPU path -- the arm this flag times -- needs a process that sees none.
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
     import torch
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core, the same count at every N
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -164,7 +171,8 @@ def run_reference(args):
     dt = (time.time() - t0) / max(1, steps)
     value = REF_SAMPLE / dt
     cb = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
-          "sample": "each step = %d images (fixed bounded sample of the 6144-image step): %s" % (REF_SAMPLE, what)}
+          "sample": "each step = %d images (fixed bounded sample of the 6144-image step): %s; os.cpu_count()=%s"
+                    % (REF_SAMPLE, what, os.cpu_count())}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
