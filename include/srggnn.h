@@ -44,6 +44,15 @@ int srg_create(srg_handle** out, int device, int D, int R, int T, int n_verbs, i
 int srg_destroy(srg_handle* h);
 int srg_set_cta_group(srg_handle* h, int cta_group);
 
+/* Row layout of the role-graph paths (srg_nouns_forward / srg_nouns_backward).  on = 1 (default): only the REAL role
+ * nodes of an image (n = encoder.get_role_count(verb) of its R slots) are materialised as rows, plus ONE shared pad row
+ * per call: pad nodes start at the zero padding_idx embedding and only see themselves (model.py:95-97,
+ * imsitu_encoder.py:223-225), so all pad nodes of a batch follow one trajectory that depends on the weights only.  The
+ * row count is a function of the verb ids, which for the predicted-verb path exist only on the device: it stays there
+ * (the kernels read it), so a step has no host synchronisation.  Logits still come out for all B*R slots.
+ * on = 0: R rows per image, as the reference lays them out (A/B measurements). */
+int srg_set_compact_rows(srg_handle* h, int on);
+
 /* imsitu_encoder.roles_to_verb_tensor_list (imsitu_encoder.py:71-89) and get_role_count (158-159) as flat host tables:
  * verb2roles[v*R + r] (pad value = n_roles), role_count[v]. */
 int srg_set_tables(srg_handle* h, const int32_t* verb2roles, const int32_t* role_count);
@@ -53,6 +62,11 @@ int srg_set_tables(srg_handle* h, const int32_t* verb2roles, const int32_t* role
  * Either output may be NULL.  Returns an error flag in *bad_verb (device int, nullable) if a verb id is out of range. */
 int srg_gather_mask(srg_handle* h, const int64_t* verb, int B, int64_t* role_idx, float* mask, int* bad_verb,
                     void* stream);
+
+/* The role-graph forward calls clamp a verb id outside [0, n_verbs) to 0 (the reference raises an IndexError,
+ * imsitu_encoder.py:172-180) and raise a device flag.  srg_check_verbs synchronises `stream`, returns an error if the
+ * flag was raised since the last check, and clears it.  Debugging aid: it costs a host synchronisation. */
+int srg_check_verbs(srg_handle* h, void* stream);
 
 /* The 7 shared GGSNN linears + both classifiers (model.py:47-56,105-111); fp32, nn.Linear layout [out, in]. */
 typedef struct srg_params {
@@ -80,22 +94,36 @@ typedef struct srg_grads {
  * Must be called after every optimizer step (weights changed) and before the forward calls. */
 int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* stream);
 
-/* Bytes of caller-provided workspace needed by one forward(+backward) pass over `rows` graph nodes
- * (rows = B*R for SRG_MODE_NOUN, B for SRG_MODE_VERB). */
+/* Bytes of caller-provided workspace needed by one forward(+backward) pass over the graph nodes of B images
+ * (B*R node slots + the shared pad row for SRG_MODE_NOUN -- sized for the worst case of R real roles per image --
+ * B nodes for SRG_MODE_VERB). */
 size_t srg_workspace_bytes(srg_handle* h, int mode, int B, int precision, int save_for_backward);
 
 /* predict_nouns minus the backbone (model.py:117-155):
  *   role gather + mask (117,147) -> node = relu(feat * role_emb[role_idx] * verb_emb[verb]) (124-144)
  *   -> GGSNN(node, mask) (151) -> Dropout + Linear (152) -> logits[B*R, ldl] (first n_labels columns valid).
- * feat: fp32 [B, D]; verb: int64 [B]; keep: uint8 [B*R, D] dropout keep-mask or NULL (eval / p == 0).
- * The gathered role ids / mask stay inside the workspace; srg_gather_mask returns them when a caller wants them. */
+ * feat: fp32 [B, D]; verb: int64 [B].
+ * Dropout (model.py:110, training mode only; drop_p = 0 or both sources NULL = identity):
+ *   keep      : explicit uint8 keep-mask [B*R, D] (parity tests), or NULL;
+ *   drop_seed : device int64 scalar; with keep == NULL the keep decisions are Bernoulli(1 - drop_p) draws of a
+ *               counter-based Philox4x32-10 generator keyed by (*drop_seed, drop_stream, slot row, column), regenerated
+ *               identically by the matching backward call -- no mask is stored or read.  drop_stream separates the
+ *               paths of one step that share a seed (FCGGNN uses 0 = verb, 1 = predicted-verb nouns, 2 = gt-verb nouns).
+ * The role ids / row layout stay inside the workspace; srg_gather_mask returns ids and mask when a caller wants them. */
 int srg_nouns_forward(srg_handle* h, const float* feat, const int64_t* verb, int B, const float* role_emb,
-                      const float* verb_emb, const uint8_t* keep, float drop_p, float* logits, int64_t ldl,
-                      int precision, int save_for_backward, void* workspace, size_t workspace_bytes, void* stream);
+                      const float* verb_emb, const uint8_t* keep, float drop_p, const int64_t* drop_seed,
+                      int64_t drop_stream, float* logits, int64_t ldl, int precision, int save_for_backward,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
-/* predict_verb minus the backbone (model.py:160-168): node = relu(feat) -> GGSNN(verb=True) -> Dropout + Linear. */
-int srg_verb_forward(srg_handle* h, const float* feat, int B, const uint8_t* keep, float drop_p, float* logits,
-                     int64_t ldl, int precision, int save_for_backward, void* workspace, size_t workspace_bytes,
+/* predict_verb minus the backbone (model.py:160-168): node = relu(feat) -> GGSNN(verb=True) -> Dropout + Linear.
+ * keep: uint8 [B, D]; dropout arguments as above. */
+int srg_verb_forward(srg_handle* h, const float* feat, int B, const uint8_t* keep, float drop_p,
+                     const int64_t* drop_seed, int64_t drop_stream, float* logits, int64_t ldl, int precision,
+                     int save_for_backward, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The keep-mask the Philox path applies for (*drop_seed, drop_stream, drop_p) on a [rows, D] slot matrix, written as
+ * uint8 0/1 (tests: lets the oracle replay exactly the dropout a training step used). */
+int srg_dropout_mask(const int64_t* drop_seed, int64_t drop_stream, float drop_p, int64_t rows, int D, uint8_t* keep,
                      void* stream);
 
 /* GGSNN.forward (model.py:59-86) on caller-provided node states: hidden fp32 [rows, D] is updated in place.
@@ -138,12 +166,15 @@ size_t srg_workspace_stats_offset(srg_handle* h, int mode, int B, int precision,
                                   const void* workspace);
 
 /* autograd backward of srg_nouns_forward / srg_verb_forward (sr.py:76-79).  `workspace` must be the one used by the
- * matching forward call with save_for_backward = 1.  dlogits: fp32 [rows, ldl].  Gradients accumulate into `g`. */
+ * matching forward call with save_for_backward = 1, and the dropout arguments must be that call's (the seed scalar
+ * must still hold the same value).  dlogits: fp32 [rows, ldl].  Gradients accumulate into `g`. */
 int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const float* feat, const int64_t* verb, int B,
                        const float* role_emb, const float* verb_emb, const uint8_t* keep, float drop_p,
-                       const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream);
+                       const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
+                       size_t workspace_bytes, void* stream);
 int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int B, const uint8_t* keep, float drop_p,
-                      const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream);
+                      const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* Deferred chain rule.  The verb node and the role graph share one GGNN (model.py:28-35, 226), so one training step
  * (sr.py:63-79) calls both backward functions with the same weights.  Their gradients w.r.t. the message-side weights

@@ -33,12 +33,15 @@ SIGNATURES = {
     "srg_create": (_i, [_c.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i]),
     "srg_destroy": (_i, [_vp]),
     "srg_set_cta_group": (_i, [_vp, _i]),
+    "srg_set_compact_rows": (_i, [_vp, _i]),
     "srg_set_tables": (_i, [_vp, _vp, _vp]),
+    "srg_check_verbs": (_i, [_vp, _vp]),
     "srg_gather_mask": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "srg_pack_weights": (_i, [_vp, _c.POINTER(SrgParams), _i, _vp]),
     "srg_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
-    "srg_nouns_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _i, _i, _vp, _sz, _vp]),
-    "srg_verb_forward": (_i, [_vp, _vp, _i, _vp, _f, _vp, _i64, _i, _i, _vp, _sz, _vp]),
+    "srg_nouns_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _vp, _i64, _i, _i, _vp, _sz, _vp]),
+    "srg_verb_forward": (_i, [_vp, _vp, _i, _vp, _f, _vp, _i64, _vp, _i64, _i, _i, _vp, _sz, _vp]),
+    "srg_dropout_mask": (_i, [_vp, _i64, _f, _i64, _i, _vp, _vp]),
     "srg_ggnn_forward": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "srg_count_targets": (_i, [_vp, _vp, _i, _vp, _vp]),
     "srg_nouns_loss": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp]),
@@ -46,9 +49,9 @@ SIGNATURES = {
     "srg_nouns_loss_backward": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "srg_verb_loss_backward": (_i, [_vp, _vp, _i64, _vp, _i, _f, _vp, _vp, _f, _vp, _vp, _vp]),
     "srg_workspace_stats_offset": (_sz, [_vp, _i, _i, _i, _i, _vp]),
-    "srg_nouns_backward": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _c.POINTER(SrgGrads), _vp, _sz,
-                                _vp]),
-    "srg_verb_backward": (_i, [_vp, _vp, _i64, _i, _vp, _f, _c.POINTER(SrgGrads), _vp, _sz, _vp]),
+    "srg_nouns_backward": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _c.POINTER(SrgGrads), _vp,
+                                _sz, _vp]),
+    "srg_verb_backward": (_i, [_vp, _vp, _i64, _i, _vp, _f, _vp, _i64, _c.POINTER(SrgGrads), _vp, _sz, _vp]),
     "srg_set_deferred_chain": (_i, [_vp, _i, _vp]),
     "srg_chain_finalize": (_i, [_vp, _c.POINTER(SrgGrads), _vp]),
     "srg_clip_adamax": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp, _vp]),

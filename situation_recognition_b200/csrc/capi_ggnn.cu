@@ -22,6 +22,7 @@ struct srg_handle {
   int device = 0, D = 0, R = 0, T = 0, V = 0, n_roles = 0, L = 0;
   int Vpad = 0, Lpad = 0;
   int cg = 2;
+  int compact = 1;      // role-node rows: 1 = real rows + ONE shared pad row (default), 0 = R rows per image
   DeviceInfo dev;
   int32_t* d_verb2roles = nullptr;
   int32_t* d_role_count = nullptr;
@@ -61,7 +62,9 @@ struct StepBufs {
 };
 
 struct PathBufs {
-  int M = 0;
+  int M = 0;       // rows the state buffers are allocated (and the tensor maps built) for
+  int Mfull = 0;   // node slots B*R (role graph) or B (verb node): the rows of the classifier GEMM and of the logits
+  RowMap rm;       // role-graph paths: device-resident compact row layout (the GEMMs read their M from rm.meta)
   float* h32 = nullptr;
   bf16* hb_hi[kMaxT + 1] = {};
   bf16* hb_mid[kMaxT + 1] = {};
@@ -69,7 +72,6 @@ struct PathBufs {
   StepBufs st[kMaxT];
   bf16 *xd_hi = nullptr, *xd_mid = nullptr, *xd_lo = nullptr;
   float* stats = nullptr;
-  float* mask = nullptr;
   // backward
   float *dh = nullptr, *dh_acc = nullptr, *dx = nullptr;
   bf16* dpre_all = nullptr;  // [T*M, 3D]: per step t (row offset t*M) the column blocks [dpre_h | dpre_z | dpre_r]
@@ -98,15 +100,26 @@ struct Bump {
 inline bool base_is_null(const void* ws) { return ws == nullptr; }
 
 // Lay the buffers of one path out in `ws` (ws == nullptr: only compute the size).
-PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* ws) {
+// rowmap: the path uses the device-resident row layout (srg_nouns_*): B*R node slots + the shared pad row, rounded up to
+// whole 256-row tiles, is the upper bound of its rows; otherwise the rows are the dense B*R / B rows of the caller.
+PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* ws, bool rowmap) {
   PathBufs pb;
   const int D = h->D, T = h->T;
-  const int M = (mode == SRG_MODE_NOUN) ? B * h->R : B;
+  const int Mfull = (mode == SRG_MODE_NOUN) ? B * h->R : B;
+  const int M = rowmap ? round_up(Mfull + 1, 256) : Mfull;
   const size_t MD = static_cast<size_t>(M) * D;
+  const size_t MfD = static_cast<size_t>(Mfull) * D;
   const bool f32 = (prec == SRG_PREC_FP32);
   const int npad = (mode == SRG_MODE_NOUN) ? h->Lpad : h->Vpad;
   Bump bump(ws);
   pb.M = M;
+  pb.Mfull = Mfull;
+  if (rowmap) {
+    pb.rm.cnt = bump.take<int>(B);
+    pb.rm.off = bump.take<int>(static_cast<size_t>(B) + 1);
+    pb.rm.meta = bump.take<int>(4);
+    pb.rm.compact = h->compact;
+  }
   pb.h32 = bump.take<float>(MD);
   // operand copies of the state, one per step boundary: ONE contiguous [(T+1)*M, D] array in training mode (the
   // weight-gradient GEMMs read steps 0..T-1 as a single K = T*M operand), two ping-pong blocks otherwise
@@ -146,20 +159,20 @@ PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* w
     st.r = r_all ? r_all + off : nullptr;
     st.hc = hc_all ? hc_all + off : nullptr;
   }
-  pb.xd_hi = bump.take<bf16>(MD);
-  pb.xd_mid = f32 ? bump.take<bf16>(MD) : nullptr;
-  pb.xd_lo = f32 ? bump.take<bf16>(MD) : nullptr;
-  pb.stats = bump.take<float>(static_cast<size_t>(M) * (npad / 128) * 2);
-  if (mode == SRG_MODE_NOUN) pb.mask = bump.take<float>(static_cast<size_t>(B) * h->R * h->R);
+  // classifier side: one row per node slot
+  pb.xd_hi = bump.take<bf16>(MfD);
+  pb.xd_mid = f32 ? bump.take<bf16>(MfD) : nullptr;
+  pb.xd_lo = f32 ? bump.take<bf16>(MfD) : nullptr;
+  pb.stats = bump.take<float>(static_cast<size_t>(Mfull) * (npad / 128) * 2);
   if (save) {
     pb.dh = bump.take<float>(MD);
     pb.dh_acc = bump.take<float>(MD);
-    pb.dx = bump.take<float>(MD);
+    pb.dx = bump.take<float>(MfD);
     pb.dpre_all = bump.take<bf16>(static_cast<size_t>(T) * 3 * MD);
     pb.da = bump.take<bf16>(MD);
     pb.ada = bump.take<bf16>(MD);
     pb.e = bump.take<bf16>(MD);
-    pb.dlb = bump.take<bf16>(static_cast<size_t>(M) * npad);
+    pb.dlb = bump.take<bf16>(static_cast<size_t>(Mfull) * npad);
     pb.G_P = bump.take<float>(static_cast<size_t>(3) * D * D);
     pb.G_Pb = bump.take<bf16>(static_cast<size_t>(3) * D * D);
     pb.s_all = bump.take<float>(static_cast<size_t>(3) * D);
@@ -168,15 +181,16 @@ PathBufs carve(const srg_handle* h, int mode, int B, int prec, int save, void* w
   return pb;
 }
 
-int check_ws(const srg_handle* h, int mode, int B, int prec, int save, void* ws, size_t ws_bytes, PathBufs* out) {
+int check_ws(const srg_handle* h, int mode, int B, int prec, int save, void* ws, size_t ws_bytes, PathBufs* out,
+             bool rowmap) {
   SRG_CHECK(h != nullptr, "null handle");
   SRG_CHECK(B > 0, "batch must be positive (got %d)", B);
   SRG_CHECK(prec == SRG_PREC_BF16 || prec == SRG_PREC_FP32, "bad precision %d", prec);
   SRG_CHECK(!(save && prec != SRG_PREC_BF16), "save_for_backward requires SRG_PREC_BF16 (the fp32 mode is forward-only)");
   SRG_CHECK(ws != nullptr, "null workspace");
   SRG_CHECK((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
-  *out = carve(h, mode, B, prec, save, ws);
-  const size_t need = carve(h, mode, B, prec, save, nullptr).bytes;
+  *out = carve(h, mode, B, prec, save, ws, rowmap);
+  const size_t need = carve(h, mode, B, prec, save, nullptr, rowmap).bytes;
   if (need > ws_bytes)
     return set_error(SRG_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
   return SRG_OK;
@@ -188,6 +202,13 @@ GemmProblem base_problem(const srg_handle* h, int M, int N) {
   p.cg = h->cg;
   p.M = M;
   p.N = N;
+  return p;
+}
+
+// a GEMM over the node rows of a path: M is the allocated upper bound, the kernel reads the actual row count
+GemmProblem path_problem(const srg_handle* h, const PathBufs& pb, int N) {
+  GemmProblem p = base_problem(h, pb.M, N);
+  p.m_dev = pb.rm.meta;   // meta[0]; nullptr = static rows
   return p;
 }
 
@@ -232,27 +253,43 @@ int wgrad_splits(const srg_handle* h, int out_rows, int out_cols, int K) {
   return s;
 }
 
-// dW[out, in] += dY^T[out, M] * X[M, in]   (both operands MN-major, split-K, TMA reduce-add).
-// dY is a column block (out_rows columns, leading dimension dy_ld) of a wider matrix.
-int wgrad(const srg_handle* h, const bf16* dY, int64_t dy_ld, int out_rows, const bf16* X, int in_cols, int M,
-          float* dW, cudaStream_t s) {
+// dW[out, in] += dY^T[out, K] * X[K, in]   (both operands MN-major, split-K, TMA reduce-add).
+// dY is a column block (out_rows columns, leading dimension dy_ld) of a wider matrix.  K runs over `nseg` row segments
+// of `seg_rows` rows each, segment t starting at row t * seg_stride of BOTH operands (the T propagation steps of a
+// path); k_dev (nullable) = device-resident number of valid rows per segment (seg_rows is then its upper bound).
+int wgrad(const srg_handle* h, const bf16* dY, int64_t dy_ld, int out_rows, const bf16* X, int in_cols, int nseg,
+          int seg_rows, int64_t seg_stride, const int* k_dev, float* dW, cudaStream_t s) {
   if (dW == nullptr) return SRG_OK;
+  const int64_t phys_rows = static_cast<int64_t>(nseg - 1) * seg_stride + seg_rows;
   GemmProblem p = base_problem(h, out_rows, in_cols);
   p.a_mn = true;
   p.b_mn = true;
-  p.nseg = 1;
-  p.seg[0].a = mat(dY, M, out_rows, dy_ld, DT_BF16);
-  p.seg[0].k_off = 0;
-  p.seg[0].k_len = M;
-  p.b = mat(X, M, in_cols, in_cols, DT_BF16);
   p.epi = EPI_STORE_F32;
   p.flags = FLAG_REDUCE;
+  if (nseg > 1 && seg_stride == seg_rows && k_dev == nullptr) {   // dense: one long K
+    nseg = 1;
+    seg_rows = static_cast<int>(phys_rows);
+  }
+  SRG_CHECK(nseg >= 1 && nseg <= kMaxSeg, "wgrad: bad segment count %d", nseg);
+  p.nseg = nseg;
+  for (int t = 0; t < nseg; ++t) {
+    p.seg[t].a = mat(dY, phys_rows, out_rows, dy_ld, DT_BF16);
+    p.seg[t].k_off = static_cast<int>(t * seg_stride);
+    p.seg[t].k_len = seg_rows;
+  }
+  if (nseg > 1 || k_dev != nullptr) p.flags |= FLAG_BK_A;
+  p.k_dev = k_dev;
+  p.b = mat(X, phys_rows, in_cols, in_cols, DT_BF16);
   p.io[0] = mat(dW, out_rows, in_cols, in_cols, DT_F32);
-  p.k_splits = wgrad_splits(h, out_rows, in_cols, M);
+  // expected K for the split heuristic: the compact layout keeps ~0.6 of the slots (imSitu: 3.55 of 6 roles)
+  const int64_t k_expect = static_cast<int64_t>(nseg) * seg_rows * ((k_dev != nullptr && h->compact) ? 3 : 5) / 5;
+  p.k_splits = wgrad_splits(h, out_rows, in_cols, static_cast<int>(k_expect));
   return run_gemm(p, h->dev, s);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+// mask: caller-provided [B,R,R] adjacency (srg_ggnn_forward on dense rows); nullptr on a role-graph path with a row map
+// (the aggregation then follows from the role counts) and on the verb node path.
 int ggnn_steps(srg_handle* h, int mode, PathBufs& pb, float* h32, const float* mask, int B, int prec, int save,
                cudaStream_t s) {
   const int D = h->D, T = h->T, M = pb.M;
@@ -265,12 +302,13 @@ int ggnn_steps(srg_handle* h, int mode, PathBufs& pb, float* h32, const float* m
     const Split3 hcur = {{pb.hb_hi[t], pb.hb_mid[t], pb.hb_lo[t]}};
     Split3 a = hcur;
     if (mode == SRG_MODE_NOUN) {
-      SRG_TRY(launch_aggregate(h32, mask, B, h->R, D, st.a_hi, st.a_mid, st.a_lo, s));
+      if (pb.rm.meta != nullptr) SRG_TRY(launch_aggregate_rows(h32, pb.rm, B, h->R, D, st.a_hi, st.a_mid, st.a_lo, s));
+      else SRG_TRY(launch_aggregate(h32, mask, B, h->R, D, st.a_hi, st.a_mid, st.a_lo, s));
       a = Split3{{st.a_hi, st.a_mid, st.a_lo}};
     }
     const Split3 rh = {{st.rh_hi, st.rh_mid, st.rh_lo}};
     {  // gates: [z | r] = sigmoid([a | h] [P_z U_z ; P_r U_r]^T + b'), rh = r * h      (model.py:74,80-81)
-      GemmProblem p = base_problem(h, M, 2 * D);
+      GemmProblem p = path_problem(h, pb, 2 * D);
       const Split3 ops[2] = {a, hcur};
       add_split_segs(p, M, D, f32, ops, 2);
       p.b = mat(h->Wzr, 2 * D, static_cast<int64_t>(2 * D) * kmul, static_cast<int64_t>(2 * D) * kmul, DT_BF16);
@@ -290,7 +328,7 @@ int ggnn_steps(srg_handle* h, int mode, PathBufs& pb, float* h32, const float* m
       SRG_TRY(run_gemm(p, h->dev, s));
     }
     {  // candidate + update: h' = h + z * (tanh([a | rh] [P_h U_h]^T + b') - h)      (model.py:82-84)
-      GemmProblem p = base_problem(h, M, D);
+      GemmProblem p = path_problem(h, pb, D);
       const Split3 ops[2] = {a, rh};
       add_split_segs(p, M, D, f32, ops, 2);
       p.b = mat(h->Wh, D, static_cast<int64_t>(2 * D) * kmul, static_cast<int64_t>(2 * D) * kmul, DT_BF16);
@@ -312,20 +350,35 @@ int ggnn_steps(srg_handle* h, int mode, PathBufs& pb, float* h32, const float* m
   return SRG_OK;
 }
 
-int classifier_forward(srg_handle* h, int mode, PathBufs& pb, const float* h32, const uint8_t* keep, float drop_p,
-                       float* logits, int64_t ldl, int prec, cudaStream_t s) {
-  const int D = h->D, M = pb.M;
+// Dropout in front of a classifier (model.py:106,110): explicit keep-mask, or Philox keyed by the device seed, or none.
+int make_drop(const uint8_t* keep, float drop_p, const int64_t* seed, int64_t stream_id, DropSpec* ds) {
+  SRG_CHECK(drop_p >= 0.f && drop_p < 1.f, "dropout probability %f out of range", drop_p);
+  *ds = DropSpec();
+  if (drop_p > 0.f && (keep != nullptr || seed != nullptr)) {
+    ds->keep = keep;
+    ds->seed = (keep == nullptr) ? reinterpret_cast<const long long*>(seed) : nullptr;
+    ds->stream = stream_id;
+    ds->thresh = static_cast<uint32_t>((1.0 - static_cast<double>(drop_p)) * 65536.0 + 0.5);
+    ds->scale = 1.0f / (1.0f - drop_p);
+  }
+  return SRG_OK;
+}
+
+int classifier_forward(srg_handle* h, int mode, PathBufs& pb, const float* h32, const DropSpec& ds, float* logits,
+                       int64_t ldl, int prec, cudaStream_t s) {
+  const int D = h->D, M = pb.Mfull;
   const bool f32 = (prec == SRG_PREC_FP32);
   const int kmul = f32 ? kSplitTerms : 1;
   const int ncls = (mode == SRG_MODE_NOUN) ? h->L : h->V;
   const int npad = (mode == SRG_MODE_NOUN) ? h->Lpad : h->Vpad;
   SRG_CHECK(ldl >= ncls && (ldl % 4) == 0, "logits leading dimension %lld must be >= %d and a multiple of 4",
             (long long)ldl, ncls);
-  SRG_CHECK(drop_p >= 0.f && drop_p < 1.f, "dropout probability %f out of range", drop_p);
+  // The classifier runs on every node slot: a dense [Mfull, D] operand is gathered from the (compact) state rows with
+  // the dropout applied per slot.  Dense rows without dropout (verb node in eval mode) read the state operand directly.
   Split3 x = {{pb.hb_hi[h->T], pb.hb_mid[h->T], pb.hb_lo[h->T]}};
-  if (keep != nullptr && drop_p > 0.f) {
-    SRG_TRY(launch_dropout_cast(h32, keep, 1.0f / (1.0f - drop_p), static_cast<int64_t>(M) * D, pb.xd_hi, pb.xd_mid,
-                                pb.xd_lo, s));
+  const bool use_drop = (ds.keep != nullptr || ds.seed != nullptr);
+  if (use_drop || pb.rm.meta != nullptr) {
+    SRG_TRY(launch_classifier_input(h32, pb.rm, h->R, M, D, ds, pb.xd_hi, pb.xd_mid, pb.xd_lo, s));
     x = Split3{{pb.xd_hi, pb.xd_mid, pb.xd_lo}};
   }
   GemmProblem p = base_problem(h, M, npad);
@@ -383,18 +436,21 @@ int chain_rule(srg_handle* h, const float* G_P, bf16* G_Pb, const float* s_all, 
 
 // ------------------------------------------------------------------------------------------------ backward
 int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, int64_t ldl, int B,
-                  const uint8_t* keep, float drop_p, const srg_grads* g, cudaStream_t s) {
-  const int D = h->D, T = h->T, M = pb.M, R = h->R;
+                  const DropSpec& ds, const srg_grads* g, cudaStream_t s) {
+  const int D = h->D, T = h->T, M = pb.M, Mf = pb.Mfull, R = h->R;
   const int ncls = (mode == SRG_MODE_NOUN) ? h->L : h->V;
   const int npad = (mode == SRG_MODE_NOUN) ? h->Lpad : h->Vpad;
   const bf16* Wc = (mode == SRG_MODE_NOUN) ? h->Wcn : h->Wcv;
   float* gWc = (mode == SRG_MODE_NOUN) ? g->Wc_noun : g->Wc_verb;
   float* gbc = (mode == SRG_MODE_NOUN) ? g->bc_noun : g->bc_verb;
-  const int64_t MD = static_cast<int64_t>(M) * D;
   const int64_t ld3 = 3 * static_cast<int64_t>(D);
   const float cmul = (mode == SRG_MODE_NOUN) ? static_cast<float>(R) : 1.f;  // how often b_p enters a message
-  const bool use_drop = (keep != nullptr && drop_p > 0.f);
-  const bf16* x = use_drop ? pb.xd_hi : pb.hb_hi[T];
+  const bool use_drop = (ds.keep != nullptr || ds.seed != nullptr);
+  const bool mapped = (pb.rm.meta != nullptr);            // role-graph path on the device-resident row layout
+  const bool gathered = use_drop || mapped;               // the classifier read pb.xd_hi (see classifier_forward)
+  const bf16* x = gathered ? pb.xd_hi : pb.hb_hi[T];
+  const int* rows_dev = mapped ? pb.rm.meta + 2 : nullptr;   // rows the tiles touch (multiple of 256)
+  const int* m_dev = mapped ? pb.rm.meta : nullptr;          // rows incl. the shared pad row
 
   // d/dP_x and the bias column sums: per call, or (deferred chain rule) shared by all paths of the step
   const bool defer = h->defer_chain;
@@ -405,19 +461,21 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
     SRG_CUDA(cudaMemsetAsync(s_all, 0, sizeof(float) * 3 * D, s));
   }
 
-  // ---- classifier (model.py:105-111,152,168)
-  SRG_TRY(launch_cast_pad(dlogits, ldl, M, ncls, npad, pb.dlb, s));
-  SRG_TRY(launch_colsum(pb.dlb, npad, M, ncls, gbc, 1.f, nullptr, 0.f, s));
-  SRG_TRY(wgrad(h, pb.dlb, npad, ncls, x, D, M, gWc, s));
+  // ---- classifier (model.py:105-111,152,168): one row per node slot
+  SRG_TRY(launch_cast_pad(dlogits, ldl, Mf, ncls, npad, pb.dlb, s));
+  SRG_TRY(launch_colsum(pb.dlb, npad, Mf, ncls, gbc, 1.f, nullptr, 0.f, s));
+  SRG_TRY(wgrad(h, pb.dlb, npad, ncls, x, D, 1, Mf, Mf, nullptr, gWc, s));
   {
-    GemmProblem p = base_problem(h, M, D);
-    add_seg(p, pb.dlb, M, npad, 0, npad);
+    GemmProblem p = base_problem(h, Mf, D);
+    add_seg(p, pb.dlb, Mf, npad, 0, npad);
     p.b_mn = true;
     p.b = mat(Wc, npad, D, D, DT_BF16);
     p.epi = EPI_STORE_F32;
-    p.io[0] = mat(use_drop ? pb.dx : pb.dh, M, D, D, DT_F32);
+    p.io[0] = mat(gathered ? pb.dx : pb.dh, Mf, D, D, DT_F32);
     SRG_TRY(run_gemm(p, h->dev, s));
-    if (use_drop) SRG_TRY(launch_dropout_bwd(pb.dx, keep, 1.0f / (1.0f - drop_p), MD, pb.dh, s));
+    // back through the dropout and the slot -> state-row gather: the pad slots of all images add up in the shared pad row
+    if (gathered) SRG_TRY(launch_classifier_input_bwd(pb.dx, pb.rm, (mode == SRG_MODE_NOUN) ? B : Mf,
+                                                      (mode == SRG_MODE_NOUN) ? R : 1, D, ds, pb.dh, s));
   }
 
   // dL/dh' of the last step comes from the classifier; from there on the GRU-gate derivatives of step t-1 are fused
@@ -425,14 +483,14 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
   // dpre_of(t) = [dpre_h | dpre_z | dpre_r] of step t as column blocks of one [M, 3D] matrix.
   float* dh_acc = pb.dh_acc;
   auto dpre_of = [&](int t) { return pb.dpre_all + static_cast<size_t>(t) * M * ld3; };
-  SRG_TRY(launch_gru_bwd_pre_ld(pb.dh, static_cast<const bf16*>(pb.st[T - 1].z), pb.st[T - 1].hc, pb.hb_hi[T - 1], M, D,
-                                dpre_of(T - 1) + D, dpre_of(T - 1), ld3, dh_acc, s));
+  SRG_TRY(launch_gru_bwd_pre_ld(pb.dh, static_cast<const bf16*>(pb.st[T - 1].z), pb.st[T - 1].hc, pb.hb_hi[T - 1], M,
+                                rows_dev, D, dpre_of(T - 1) + D, dpre_of(T - 1), ld3, dh_acc, s));
   for (int t = T - 1; t >= 0; --t) {
     StepBufs& st = pb.st[t];
     bf16* dp = dpre_of(t);
     bf16* dpre_r = dp + 2 * D;   // column blocks of dp: [dpre_h | dpre_z | dpre_r]
     {  // d(r*h) = dpre_h U_h ; fused: dpre_r = drh*h*r*(1-r), e = drh*r (this path's share of dL/dh)
-      GemmProblem p = base_problem(h, M, D);
+      GemmProblem p = path_problem(h, pb, D);
       add_seg_ld(p, dp, M, ld3, ld3, 0, D);
       p.b_mn = true;
       p.b = mat(h->Uh, D, D, D, DT_BF16);
@@ -444,7 +502,7 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
       SRG_TRY(run_gemm(p, h->dev, s));
     }
     {  // da = [dpre_h | dpre_z | dpre_r] [P_h ; P_z ; P_r]   (gradient w.r.t. the aggregated state)
-      GemmProblem p = base_problem(h, M, D);
+      GemmProblem p = path_problem(h, pb, D);
       add_seg_ld(p, dp, M, ld3, ld3, 0, 3 * D);
       p.b_mn = true;
       p.b = mat(h->P_hi, 3 * D, D, D, DT_BF16);
@@ -452,13 +510,12 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
       p.io[0] = mat(pb.da, M, D, D, DT_BF16);
       SRG_TRY(run_gemm(p, h->dev, s));
     }
-    // back through the aggregation, plus the r*h share:  ada[b,j] = e[b,j] + sum_i mask[b,i,j] da[b,i]
-    // (verb node: the aggregation is the identity, mask == nullptr)
-    SRG_TRY(launch_aggregate_t_bf16(pb.da, (mode == SRG_MODE_NOUN) ? pb.mask : nullptr, pb.e,
-                                    (mode == SRG_MODE_NOUN) ? B : M, (mode == SRG_MODE_NOUN) ? R : 1, D, pb.ada, s));
+    // back through the aggregation, plus the r*h share:  ada[j] = e[j] + sum_i mask[i,j] da[i]
+    // (verb node: the aggregation is the identity)
+    SRG_TRY(launch_aggregate_t_rows(pb.da, pb.e, pb.rm, mapped ? B : M, R, D, pb.ada, s));
     const bf16* ada = pb.ada;
     {  // dL/dh_t = dh_acc + ada + [dpre_z | dpre_r] [U_z ; U_r], then the gate derivatives of step t-1
-      GemmProblem p = base_problem(h, M, D);
+      GemmProblem p = path_problem(h, pb, D);
       add_seg_ld(p, dp, M, ld3, ld3, D, 2 * D);
       p.b_mn = true;
       p.b = mat(h->U_stack, 2 * D, D, D, DT_BF16);
@@ -478,19 +535,21 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
       SRG_TRY(run_gemm(p, h->dev, s));
     }
   }
-  // ---- weight gradients: one GEMM per weight group, contracting over all T steps at once (K = T*M rows)
+  // ---- weight gradients: one GEMM per weight group, contracting over all T steps at once.  Step t occupies rows
+  // [t*M, t*M + rows) of every stash array; on the device-resident layout `rows` is read by the kernel and the rows
+  // between it and the next k-block boundary hold dpre = 0 (their dL/dh is 0 from k_zero_self_rows on).
   {
-    const int KM = T * M;
     bf16* dp = pb.dpre_all;
-    const bf16* a_all = (mode == SRG_MODE_NOUN) ? pb.st[0].a_hi : pb.hb_hi[0];   // contiguous over t = 0..T-1
-    SRG_TRY(wgrad(h, dp, ld3, 3 * D, a_all, D, KM, G_P, s));                 // dP_h, dP_z, dP_r in one GEMM
-    SRG_TRY(wgrad(h, dp + D, ld3, D, pb.hb_hi[0], D, KM, g->U_z, s));
-    SRG_TRY(wgrad(h, dp + 2 * D, ld3, D, pb.hb_hi[0], D, KM, g->U_r, s));
-    SRG_TRY(wgrad(h, dp, ld3, D, pb.st[0].rh_hi, D, KM, g->U_h, s));
+    const bf16* a_all = (mode == SRG_MODE_NOUN) ? pb.st[0].a_hi : pb.hb_hi[0];   // step t at row offset t*M
+    SRG_TRY(wgrad(h, dp, ld3, 3 * D, a_all, D, T, M, M, m_dev, G_P, s));                 // dP_h, dP_z, dP_r in one GEMM
+    SRG_TRY(wgrad(h, dp + D, ld3, D, pb.hb_hi[0], D, T, M, M, m_dev, g->U_z, s));
+    SRG_TRY(wgrad(h, dp + 2 * D, ld3, D, pb.hb_hi[0], D, T, M, M, m_dev, g->U_r, s));
+    SRG_TRY(wgrad(h, dp, ld3, D, pb.st[0].rh_hi, D, T, M, M, m_dev, g->U_h, s));
     ColsumJob jobs[3] = {{dp, g->b_Wh, g->b_Uh, 1.f, s_all, cmul},
                          {dp + D, g->b_Wz, g->b_Uz, 1.f, s_all + D, cmul},
                          {dp + 2 * D, g->b_Wr, g->b_Ur, 1.f, s_all + 2 * D, cmul}};
-    SRG_TRY(launch_colsum_multi(jobs, 3, ld3, KM, D, s));
+    if (mapped) SRG_TRY(launch_colsum_multi(jobs, 3, ld3, M, m_dev, T, M, D, s));
+    else SRG_TRY(launch_colsum_multi(jobs, 3, ld3, T * M, nullptr, 1, 0, D, s));
   }
   pb.dh = dh_acc;  // gradient w.r.t. the initial node states
 
@@ -569,6 +628,7 @@ int srg_create(srg_handle** out, int device, int D, int R, int T, int n_verbs, i
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_verb2roles), sizeof(int32_t) * n_verbs * R);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->d_role_count), sizeof(int32_t) * n_verbs);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->d_bad), sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(h->d_bad, 0, sizeof(int));
   if (e != cudaSuccess) {
     delete h;
     return set_error(SRG_ERR_CUDA, "srg_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -593,6 +653,12 @@ int srg_set_cta_group(srg_handle* h, int cta_group) {
   SRG_CHECK(h != nullptr, "null handle");
   SRG_CHECK(cta_group == 1 || cta_group == 2, "cta_group must be 1 or 2");
   h->cg = cta_group;
+  return SRG_OK;
+}
+
+int srg_set_compact_rows(srg_handle* h, int on) {
+  SRG_CHECK(h != nullptr, "null handle");
+  h->compact = (on != 0);
   return SRG_OK;
 }
 
@@ -623,6 +689,18 @@ int srg_gather_mask(srg_handle* h, const int64_t* verb, int B, int64_t* role_idx
   SRG_CHECK(verb != nullptr, "null verb pointer");
   return launch_gather_mask(h->d_verb2roles, h->d_role_count, h->V, h->R, verb, B, role_idx, mask, bad_verb,
                             static_cast<cudaStream_t>(stream));
+}
+
+int srg_check_verbs(srg_handle* h, void* stream) {
+  SRG_CHECK(h != nullptr, "srg_check_verbs: null handle");
+  DeviceGuard guard_(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int bad = 0;
+  SRG_CUDA(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SRG_CUDA(cudaMemsetAsync(h->d_bad, 0, sizeof(int), s));
+  SRG_CUDA(cudaStreamSynchronize(s));
+  if (bad) return set_error(SRG_ERR_ARG, "a verb id outside [0, %d) was passed to srg_nouns_forward (it was computed as verb 0)", h->V);
+  return SRG_OK;
 }
 
 int srg_pack_weights(srg_handle* h, const srg_params* p, int precision, void* stream) {
@@ -724,46 +802,53 @@ size_t srg_workspace_stats_offset(srg_handle* h, int mode, int B, int precision,
                                   const void* workspace) {
   if (!h || B <= 0 || !workspace) return 0;
   // carve() only does pointer arithmetic; the offset depends on the alignment of the actual workspace address
-  PathBufs pb = carve(h, mode, B, precision, save_for_backward, const_cast<void*>(workspace));
+  PathBufs pb = carve(h, mode, B, precision, save_for_backward, const_cast<void*>(workspace), mode == SRG_MODE_NOUN);
   return static_cast<size_t>(reinterpret_cast<const uint8_t*>(pb.stats) - static_cast<const uint8_t*>(workspace));
 }
 
 size_t srg_workspace_bytes(srg_handle* h, int mode, int B, int precision, int save_for_backward) {
   if (!h || B <= 0) return 0;
-  return carve(h, mode, B, precision, save_for_backward, nullptr).bytes;
+  // role-graph paths: the row-mapped layout of srg_nouns_* is the larger one (srg_ggnn_forward uses dense rows)
+  return carve(h, mode, B, precision, save_for_backward, nullptr, mode == SRG_MODE_NOUN).bytes;
 }
 
 int srg_nouns_forward(srg_handle* h, const float* feat, const int64_t* verb, int B, const float* role_emb,
-                      const float* verb_emb, const uint8_t* keep, float drop_p, float* logits, int64_t ldl,
-                      int precision, int save_for_backward, void* workspace, size_t workspace_bytes, void* stream) {
+                      const float* verb_emb, const uint8_t* keep, float drop_p, const int64_t* drop_seed,
+                      int64_t drop_stream, float* logits, int64_t ldl, int precision, int save_for_backward,
+                      void* workspace, size_t workspace_bytes, void* stream) {
   SRG_CHECK(h != nullptr, "srg_nouns_forward: null handle");
   DeviceGuard guard_(h->device);
   PathBufs pb;
-  SRG_TRY(check_ws(h, SRG_MODE_NOUN, B, precision, save_for_backward, workspace, workspace_bytes, &pb));
+  SRG_TRY(check_ws(h, SRG_MODE_NOUN, B, precision, save_for_backward, workspace, workspace_bytes, &pb, true));
   SRG_CHECK(h->tables_set, "srg_nouns_forward: call srg_set_tables first");
   SRG_CHECK(h->packed_prec == precision, "srg_nouns_forward: weights are not packed for precision %d", precision);
   SRG_CHECK(feat && verb && role_emb && verb_emb && logits, "srg_nouns_forward: null argument");
+  DropSpec ds;
+  SRG_TRY(make_drop(keep, drop_p, drop_seed, drop_stream, &ds));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  SRG_TRY(launch_gather_mask(h->d_verb2roles, h->d_role_count, h->V, h->R, verb, B, nullptr, pb.mask, nullptr, s));
-  SRG_TRY(launch_node_init_noun(feat, role_emb, verb_emb, verb, h->d_verb2roles, h->V, B, h->R, h->D, pb.h32,
+  // role counts -> compact row layout (device-resident: the predicted verbs never visit the host)
+  SRG_TRY(launch_prep_rows(h->d_role_count, h->V, h->R, verb, B, h->compact, pb.rm, h->d_bad, s));
+  SRG_TRY(launch_node_init_noun(feat, role_emb, verb_emb, verb, h->d_verb2roles, h->V, B, h->R, h->D, pb.rm, pb.h32,
                                 pb.hb_hi[0], pb.hb_mid[0], pb.hb_lo[0], s));
-  SRG_TRY(ggnn_steps(h, SRG_MODE_NOUN, pb, pb.h32, pb.mask, B, precision, save_for_backward, s));
-  return classifier_forward(h, SRG_MODE_NOUN, pb, pb.h32, keep, drop_p, logits, ldl, precision, s);
+  SRG_TRY(ggnn_steps(h, SRG_MODE_NOUN, pb, pb.h32, nullptr, B, precision, save_for_backward, s));
+  return classifier_forward(h, SRG_MODE_NOUN, pb, pb.h32, ds, logits, ldl, precision, s);
 }
 
-int srg_verb_forward(srg_handle* h, const float* feat, int B, const uint8_t* keep, float drop_p, float* logits,
-                     int64_t ldl, int precision, int save_for_backward, void* workspace, size_t workspace_bytes,
-                     void* stream) {
+int srg_verb_forward(srg_handle* h, const float* feat, int B, const uint8_t* keep, float drop_p,
+                     const int64_t* drop_seed, int64_t drop_stream, float* logits, int64_t ldl, int precision,
+                     int save_for_backward, void* workspace, size_t workspace_bytes, void* stream) {
   SRG_CHECK(h != nullptr, "srg_verb_forward: null handle");
   DeviceGuard guard_(h->device);
   PathBufs pb;
-  SRG_TRY(check_ws(h, SRG_MODE_VERB, B, precision, save_for_backward, workspace, workspace_bytes, &pb));
+  SRG_TRY(check_ws(h, SRG_MODE_VERB, B, precision, save_for_backward, workspace, workspace_bytes, &pb, false));
   SRG_CHECK(h->packed_prec == precision, "srg_verb_forward: weights are not packed for precision %d", precision);
   SRG_CHECK(feat && logits, "srg_verb_forward: null argument");
+  DropSpec ds;
+  SRG_TRY(make_drop(keep, drop_p, drop_seed, drop_stream, &ds));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SRG_TRY(launch_node_init_verb(feat, B, h->D, pb.h32, pb.hb_hi[0], pb.hb_mid[0], pb.hb_lo[0], s));
   SRG_TRY(ggnn_steps(h, SRG_MODE_VERB, pb, pb.h32, nullptr, B, precision, save_for_backward, s));
-  return classifier_forward(h, SRG_MODE_VERB, pb, pb.h32, keep, drop_p, logits, ldl, precision, s);
+  return classifier_forward(h, SRG_MODE_VERB, pb, pb.h32, ds, logits, ldl, precision, s);
 }
 
 int srg_ggnn_forward(srg_handle* h, int mode, float* hidden, const float* mask, int B, int precision,
@@ -772,13 +857,26 @@ int srg_ggnn_forward(srg_handle* h, int mode, float* hidden, const float* mask, 
   DeviceGuard guard_(h->device);
   PathBufs pb;
   SRG_CHECK(mode == SRG_MODE_NOUN || mode == SRG_MODE_VERB, "bad mode %d", mode);
-  SRG_TRY(check_ws(h, mode, B, precision, save_for_backward, workspace, workspace_bytes, &pb));
+  SRG_TRY(check_ws(h, mode, B, precision, save_for_backward, workspace, workspace_bytes, &pb, false));
   SRG_CHECK(h->packed_prec == precision, "srg_ggnn_forward: weights are not packed for precision %d", precision);
   SRG_CHECK(hidden != nullptr, "null hidden state");
   SRG_CHECK(mode == SRG_MODE_VERB || mask != nullptr, "noun mode needs a mask");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SRG_TRY(launch_split_cast(hidden, static_cast<int64_t>(pb.M) * h->D, pb.hb_hi[0], pb.hb_mid[0], pb.hb_lo[0], s));
   return ggnn_steps(h, mode, pb, hidden, mask, B, precision, save_for_backward, s);
+}
+
+int srg_dropout_mask(const int64_t* drop_seed, int64_t drop_stream, float drop_p, int64_t rows, int D, uint8_t* keep,
+                     void* stream) {
+  SRG_CHECK(drop_seed != nullptr && keep != nullptr, "srg_dropout_mask: null argument");
+  SRG_CHECK(rows >= 0 && D > 0 && D % 8 == 0, "srg_dropout_mask: bad shape");
+  DropSpec ds;
+  SRG_TRY(make_drop(nullptr, drop_p, drop_seed, drop_stream, &ds));
+  if (ds.seed == nullptr) {   // p == 0: everything is kept
+    SRG_CUDA(cudaMemsetAsync(keep, 1, static_cast<size_t>(rows) * D, static_cast<cudaStream_t>(stream)));
+    return SRG_OK;
+  }
+  return launch_dropout_mask(ds, rows, D, keep, static_cast<cudaStream_t>(stream));
 }
 
 int srg_count_targets(srg_handle* h, const int64_t* gt_nouns, int B, float* counts, void* stream) {
@@ -874,32 +972,38 @@ int srg_chain_finalize(srg_handle* h, const srg_grads* g, void* stream) {
 
 int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const float* feat, const int64_t* verb, int B,
                        const float* role_emb, const float* verb_emb, const uint8_t* keep, float drop_p,
-                       const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
+                       const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
+                       size_t workspace_bytes, void* stream) {
   SRG_CHECK(h != nullptr, "srg_nouns_backward: null handle");
   DeviceGuard guard_(h->device);
   PathBufs pb;
-  SRG_TRY(check_ws(h, SRG_MODE_NOUN, B, SRG_PREC_BF16, 1, workspace, workspace_bytes, &pb));
+  SRG_TRY(check_ws(h, SRG_MODE_NOUN, B, SRG_PREC_BF16, 1, workspace, workspace_bytes, &pb, true));
   SRG_CHECK(h->packed_prec == SRG_PREC_BF16, "backward needs bf16-packed weights");
   SRG_CHECK(dlogits && feat && verb && role_emb && verb_emb && g, "srg_nouns_backward: null argument");
   SRG_CHECK(ldl >= h->L, "srg_nouns_backward: ldl %lld < n_labels %d", (long long)ldl, h->L);
+  DropSpec ds;
+  SRG_TRY(make_drop(keep, drop_p, drop_seed, drop_stream, &ds));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  SRG_TRY(path_backward(h, SRG_MODE_NOUN, pb, dlogits, ldl, B, keep, drop_p, g, s));
+  SRG_TRY(path_backward(h, SRG_MODE_NOUN, pb, dlogits, ldl, B, ds, g, s));
   if (g->role_emb != nullptr && g->verb_emb != nullptr)
     SRG_TRY(launch_node_init_bwd(pb.dh, pb.hb_hi[0], feat, role_emb, verb_emb, verb, h->d_verb2roles, h->V, h->n_roles, B,
-                                 h->R, h->D, g->role_emb, g->verb_emb, s));
+                                 h->R, h->D, pb.rm, g->role_emb, g->verb_emb, s));
   return SRG_OK;
 }
 
 int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int B, const uint8_t* keep, float drop_p,
-                      const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
+                      const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
+                      size_t workspace_bytes, void* stream) {
   SRG_CHECK(h != nullptr, "srg_verb_backward: null handle");
   DeviceGuard guard_(h->device);
   PathBufs pb;
-  SRG_TRY(check_ws(h, SRG_MODE_VERB, B, SRG_PREC_BF16, 1, workspace, workspace_bytes, &pb));
+  SRG_TRY(check_ws(h, SRG_MODE_VERB, B, SRG_PREC_BF16, 1, workspace, workspace_bytes, &pb, false));
   SRG_CHECK(h->packed_prec == SRG_PREC_BF16, "backward needs bf16-packed weights");
   SRG_CHECK(dlogits && g, "srg_verb_backward: null argument");
   SRG_CHECK(ldl >= h->V, "srg_verb_backward: ldl %lld < n_verbs %d", (long long)ldl, h->V);
-  return path_backward(h, SRG_MODE_VERB, pb, dlogits, ldl, B, keep, drop_p, g, static_cast<cudaStream_t>(stream));
+  DropSpec ds;
+  SRG_TRY(make_drop(keep, drop_p, drop_seed, drop_stream, &ds));
+  return path_backward(h, SRG_MODE_VERB, pb, dlogits, ldl, B, ds, g, static_cast<cudaStream_t>(stream));
 }
 
 #ifdef SRG_EPI_TIMING

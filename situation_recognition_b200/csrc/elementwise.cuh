@@ -10,13 +10,54 @@ namespace srg {
 
 typedef __nv_bfloat16 bf16;
 
+// Compact row layout of a role-graph path, built on the device by launch_prep_rows (all pointers are device pointers):
+//   cnt[b]  = number of real roles n_b of image b's verb            off[b] = first row of image b (off[B] = sum L_b)
+//   meta[0] = rows incl. the ONE shared pad row (the GEMMs' M)      meta[1] = index of the shared pad row
+//   meta[2] = meta[0] rounded up to 256: the rows the GEMM tiles touch; every one of them holds finite values
+// compact = 1: image b owns L_b = n_b rows (pad nodes are not materialised: they all follow the shared pad row's
+// trajectory); compact = 0: L_b = R rows per image as the reference lays them out (kept for A/B measurements).
+// All members null: the path has a static dense row layout (verb node path, srg_ggnn_forward).
+struct RowMap {
+  const int* cnt = nullptr;
+  const int* off = nullptr;
+  const int* meta = nullptr;
+  int compact = 0;
+};
+
+// Dropout in front of a classifier: explicit uint8 keep-mask [rows, D] (tests), or Philox keyed by (*seed, stream, row,
+// column); neither: identity.  thresh = (1 - p) * 65536, scale = 1 / (1 - p).
+struct DropSpec {
+  const uint8_t* keep = nullptr;
+  const long long* seed = nullptr;
+  long long stream = 0;
+  uint32_t thresh = 65536;
+  float scale = 1.f;
+};
+
 int launch_gather_mask(const int32_t* verb2roles, const int32_t* role_count, int n_verbs, int R, const int64_t* verb,
                        int B, int64_t* role_idx, float* mask, int* bad, cudaStream_t s);
 
-// node[b*R+r, :] = relu(feat[b,:] * role_emb[verb2roles[verb[b], r], :] * verb_emb[verb[b], :])   (model.py:124-144)
+// cnt / off / meta of `rm` from the verb ids (imsitu_encoder.py:158-159 per image + an exclusive scan); one block
+int launch_prep_rows(const int32_t* role_count, int n_verbs, int R, const int64_t* verb, int B, int compact, RowMap rm,
+                     int* bad, cudaStream_t s);
+// node[row(b,r), :] = relu(feat[b,:] * role_emb[verb2roles[verb[b], r], :] * verb_emb[verb[b], :])   (model.py:124-144)
+// for the rows `rm` materialises; the self-loop rows are set to 0
 int launch_node_init_noun(const float* feat, const float* role_emb, const float* verb_emb, const int64_t* verb,
-                          const int32_t* verb2roles, int n_verbs, int B, int R, int D, float* h32, bf16* hb_hi,
-                          bf16* hb_mid, bf16* hb_lo, cudaStream_t s);
+                          const int32_t* verb2roles, int n_verbs, int B, int R, int D, RowMap rm, float* h32,
+                          bf16* hb_hi, bf16* hb_mid, bf16* hb_lo, cudaStream_t s);
+// the same aggregation as launch_aggregate on the rows of `rm`, from the role counts instead of a [B,R,R] mask
+int launch_aggregate_rows(const float* h32, RowMap rm, int B, int R, int D, bf16* a_hi, bf16* a_mid, bf16* a_lo,
+                          cudaStream_t s);
+// ada = e + aggregate^T(da) on the rows of `rm` (rm.cnt == nullptr: B dense rows, identity aggregation)
+int launch_aggregate_t_rows(const bf16* da, const bf16* e, RowMap rm, int B, int R, int D, bf16* ada, cudaStream_t s);
+// x[row] = dropout(h32[row of slot `row` under rm]) for all `rows` node slots -> bf16 hi (+ mid, lo)
+int launch_classifier_input(const float* h32, RowMap rm, int R, int64_t rows, int D, DropSpec ds, bf16* x_hi,
+                            bf16* x_mid, bf16* x_lo, cudaStream_t s);
+// dh[row under rm] = dropout'(dx[slot]) with all pad slots summed into the shared pad row
+int launch_classifier_input_bwd(const float* dx, RowMap rm, int B, int R, int D, DropSpec ds, float* dh,
+                                cudaStream_t s);
+// out[rows, D] uint8 = the keep decisions `ds` makes (tests: feeds the oracle the mask the Philox path used)
+int launch_dropout_mask(DropSpec ds, int64_t rows, int D, uint8_t* out, cudaStream_t s);
 // node = relu(feat)  (model.py:160)
 int launch_node_init_verb(const float* feat, int B, int D, float* h32, bf16* hb_hi, bf16* hb_mid, bf16* hb_lo,
                           cudaStream_t s);
@@ -41,12 +82,6 @@ int launch_pack_weight_multi(const PackJob* jobs, int n_jobs, int cols, cudaStre
 // dst[i] = a[i] (+ b[i]) for i < n, 0 for n <= i < n_pad
 int launch_pack_bias(const float* a, const float* b, int n, int n_pad, float* dst, cudaStream_t s);
 
-// x = h * keep / (1-p)  -> bf16 hi (+lo)
-int launch_dropout_cast(const float* h32, const uint8_t* keep, float scale, int64_t n, bf16* hi, bf16* mid, bf16* lo,
-                        cudaStream_t s);
-// dh = dx * keep / (1-p)   (keep may be null)
-int launch_dropout_bwd(const float* dx, const uint8_t* keep, float scale, int64_t n, float* dh, cudaStream_t s);
-
 int launch_count_targets(const int64_t* gt, int B, int R, int ignore_index, float* counts, cudaStream_t s);
 // one warp per logits row; loss and dlogits are both optional; the gradient is scaled by grad_scale and, when
 // gscale_dev is not null, by that device scalar as well
@@ -65,11 +100,9 @@ int launch_colsum(const bf16* X, int64_t ld, int rows, int n_cols, float* out1, 
 // node-init backward (embedding gradients), model.py:132-144
 int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, const float* role_emb,
                          const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_verbs,
-                         int n_roles, int B, int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s);
+                         int n_roles, int B, int R, int D, RowMap rm, float* d_role_emb, float* d_verb_emb,
+                         cudaStream_t s);
 
-// adm[b,j,:] = add[b,j,:] + sum_i mask[b,i,j] * dm[b,i,:]   (bf16 in / bf16 out; mask == nullptr: identity, R = 1)
-int launch_aggregate_t_bf16(const bf16* dm, const float* mask, const bf16* add, int B, int R, int D, bf16* adm,
-                            cudaStream_t s);
 // up to 4 column sums in one launch: out1/out2 += scale * colsum, out3 += scale3 * colsum
 struct ColsumJob {
   const bf16* X;
@@ -79,7 +112,10 @@ struct ColsumJob {
   float* out3;
   float scale3;
 };
-int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows, int n_cols, cudaStream_t s);
+// rows: nseg segments of `rows` rows (rows_dev, nullable: device count of valid rows per segment), segment s at row
+// s * seg_stride of X
+int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows, const int* rows_dev, int nseg,
+                        int64_t seg_stride, int n_cols, cudaStream_t s);
 
 
 // clip_grad_norm_(max_norm) + Adamax on flat fp32 buffers (sr.py:80-83).  scratch: device fp32 [2] = {sum g^2, step}.
@@ -87,8 +123,9 @@ int launch_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_i
                        float beta2, float eps, float max_norm, float* norm_sq, float* step, cudaStream_t s);
 
 // GRU backward prologue writing into column blocks of a wider matrix (leading dimension ld_out elements)
-int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int rows, int D,
-                          bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc, cudaStream_t s);
+// rows_dev (nullable): device count of rows, overrides `rows` (which then only sizes the grid)
+int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int rows, const int* rows_dev,
+                          int D, bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc, cudaStream_t s);
 // y[o] = sum_k W[o,k] x[k]                       (fp32, W row-major [rows, cols])
 int launch_matvec(const float* W, const float* x, int rows, int cols, float* y, cudaStream_t s);
 // y[k] += sum_x sum_o W_x[o,k] s[x*rows + o]    (three [rows, cols] matrices in one launch; null W_x skipped)

@@ -40,7 +40,9 @@ enum EpiKind : int {
   EPI_DH = 6,          // backward: g = acc + dh_acc = dL/dh_{t-1}'; fused GRU-gate derivatives of step t-1
 };
 
-enum : int { FLAG_LO = 1, FLAG_STASH = 2, FLAG_REDUCE = 4, FLAG_NEXT = 8, FLAG_ADD = 16 };
+// FLAG_BK_A: the K coordinate of B follows A's (both operands are row blocks of equally laid out activations: the
+// weight-gradient GEMMs over K segments), instead of running contiguously through a packed B
+enum : int { FLAG_LO = 1, FLAG_STASH = 2, FLAG_REDUCE = 4, FLAG_NEXT = 8, FLAG_ADD = 16, FLAG_BK_A = 32 };
 
 struct GemmMaps {
   CUtensorMap a[kMaxAMaps];
@@ -50,6 +52,12 @@ struct GemmMaps {
 
 struct GemmArgs {
   int M, N;
+  // Device-resident problem sizes (nullable).  The compact role-node layout makes the number of node rows a function of
+  // the batch's verbs, which for the predicted-verb path only exist on the device: the host sizes descriptors, buffers
+  // and the grid for the upper bound and the kernel reads the actual count, so a step needs no host synchronisation and
+  // can be replayed from a CUDA graph.
+  const int* m_dev;   // rows of D (overrides M; M stays the upper bound the tensor maps were built for)
+  const int* k_dev;   // rows of EVERY K segment (overrides seg_kb / total_kb; rounded up to whole k-blocks)
   int nseg;
   int seg_map[kMaxSeg];
   int seg_acol[kMaxSeg];  // start coordinate along K inside the A map (elements)
@@ -250,11 +258,14 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
   const int cluster_id = (CG == 2) ? static_cast<int>(ptx::cluster_id_x()) : static_cast<int>(blockIdx.x);
   const int num_clusters = (CG == 2) ? static_cast<int>(ptx::num_clusters_x()) : static_cast<int>(gridDim.x);
 
-  // work decomposition
-  const int num_m_tiles = (args.M + kTileM * CG - 1) / (kTileM * CG);
+  // work decomposition (the sizes may live on the device, see GemmArgs)
+  const int M_rt = (args.m_dev != nullptr) ? __ldg(args.m_dev) : args.M;
+  const int seg_kb_rt = (args.k_dev != nullptr) ? (__ldg(args.k_dev) + kBlockK - 1) / kBlockK : 0;
+  const int total_kb = (args.k_dev != nullptr) ? seg_kb_rt * args.nseg : args.total_kb;
+  const int num_m_tiles = (M_rt + kTileM * CG - 1) / (kTileM * CG);
   const int num_n_tiles = args.N / BLOCK_N;
-  const int k_splits = args.k_splits;
-  const int kb_per_split = (args.total_kb + k_splits - 1) / k_splits;
+  const int kb_per_split = (total_kb + args.k_splits - 1) / args.k_splits;
+  const int k_splits = (total_kb + kb_per_split - 1) / max(kb_per_split, 1);   // every split owns >= 1 k-block
   const int tiles_mn = num_m_tiles * num_n_tiles;
   const int total_work = tiles_mn * k_splits;
 
@@ -294,20 +305,27 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
         const int m0 = mt * kTileM * CG + static_cast<int>(cta_rank) * kTileM;
         const int nb0 = nt * BLOCK_N + static_cast<int>(cta_rank) * B_ROWS;
         const int kb_begin = ks * kb_per_split;
-        const int kb_end = min(args.total_kb, kb_begin + kb_per_split);
+        const int kb_end = min(total_kb, kb_begin + kb_per_split);
         // locate the first segment
         int seg = 0, seg_first = 0;
-        while (seg < args.nseg - 1 && kb_begin >= seg_first + args.seg_kb[seg]) {
-          seg_first += args.seg_kb[seg];
-          ++seg;
-        }
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          while (seg < args.nseg - 1 && kb >= seg_first + args.seg_kb[seg]) {
+        if (seg_kb_rt == 0) {
+          while (seg < args.nseg - 1 && kb_begin >= seg_first + args.seg_kb[seg]) {
             seg_first += args.seg_kb[seg];
             ++seg;
           }
+        }
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (seg_kb_rt != 0) {               // equally long segments of device-resident length
+            seg = kb / seg_kb_rt;
+            seg_first = seg * seg_kb_rt;
+          } else {
+            while (seg < args.nseg - 1 && kb >= seg_first + args.seg_kb[seg]) {
+              seg_first += args.seg_kb[seg];
+              ++seg;
+            }
+          }
           const int ka = args.seg_acol[seg] + (kb - seg_first) * kBlockK;
-          const int kbcoord = kb * kBlockK;
+          const int kbcoord = (args.flags & FLAG_BK_A) ? ka : kb * kBlockK;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem_a + stage * A_BYTES;
           uint8_t* sb = smem_b + stage * B_BYTES;
@@ -367,7 +385,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
       for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
         const int ks = w / tiles_mn;
         const int kb_begin = ks * kb_per_split;
-        const int kb_end = min(args.total_kb, kb_begin + kb_per_split);
+        const int kb_end = min(total_kb, kb_begin + kb_per_split);
         // F32 (parity) instantiations use the two TMEM accumulators of ONE tile: the leading hi*hi terms go to the
         // first, the small split-correction terms to the second (they are summed in fp32 in the epilogue).  The tensor
         // core truncates when it adds into the accumulator, so keeping the ~2^-9-sized corrections out of the large
@@ -437,7 +455,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
         const int row0 = row_of(w), n0 = n0_of(w);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
-        const bool active = row0 < args.M;       // CTA-uniform: TMA clips a partially valid tile itself
+        const bool active = row0 < M_rt;         // CTA-uniform: TMA clips a partially valid tile itself
         const bool tin = needs_in(n0);
         const bool r_tile = (EPI == EPI_ZR) && tin;
         const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
@@ -459,7 +477,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
             if (ncc == NCH) {
               nw = w + num_clusters;
               ncc = 0;
-              nvalid = (nw < total_work) && (row_of(nw) < args.M);
+              nvalid = (nw < total_work) && (row_of(nw) < M_rt);
             }
             const bool pre = nvalid && needs_in(n0_of(nw));
             SRG_T(c0);
@@ -528,16 +546,21 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
     for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
       const int nt = (w % tiles_mn) % num_n_tiles;
       const int mt = (w % tiles_mn) / num_n_tiles;
-      const int row0 = mt * kTileM * CG + static_cast<int>(cta_rank) * kTileM + ew * 32;  // first row of this warp
+      const int cta_row0 = mt * kTileM * CG + static_cast<int>(cta_rank) * kTileM;
+      const int row0 = cta_row0 + ew * 32;  // first row of this warp
       const int n0 = nt * BLOCK_N;
       const int acc = F32 ? 0 : (iter & 1);
       const uint32_t acc_phase = F32 ? (iter & 1) : ((iter >> 1) & 1);
-      const bool warp_active = row0 < args.M;  // TMA clips partially valid boxes itself
+      // Static M: the tensor maps end at row M, TMA clips partially valid boxes itself and a warp whose rows all lie
+      // beyond M has nothing to do.  Device-resident M: the maps cover the allocated upper bound, and every row of a CTA
+      // tile that holds at least one valid row is written -- downstream kernels treat the rows up to the tile boundary
+      // as defined (zero-gradient "self-loop" rows of the compact role-node layout, see k_prep_rows).
+      const bool warp_active = (args.m_dev != nullptr) ? (cta_row0 < M_rt) : (row0 < M_rt);
 
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
-      const bool has_corr = F32 && args.corr_kb_begin < args.total_kb;
+      const bool has_corr = F32 && args.corr_kb_begin < total_kb;
       // 32 accumulator columns of this lane's row (main + correction accumulator in the parity instantiations)
       auto load_acc = [&](int col, float (&v)[32]) {
         ptx::tmem_ld_32x32(tacc + col, v);
@@ -803,7 +826,7 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
 
       if constexpr (EPI == EPI_LOGITS) {
         const int row = row0 + lane;
-        if (row < args.M) {
+        if (row < M_rt) {
           float2* st = reinterpret_cast<float2*>(args.stats) + static_cast<size_t>(row) * num_n_tiles + nt;
           *st = make_float2(st_max, st_sum);
         }

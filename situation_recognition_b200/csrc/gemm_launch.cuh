@@ -1,6 +1,7 @@
 // GEMM launcher: maps a problem description onto one gemm_kernel instantiation (descriptor encoding + dispatch).
 // Included by exactly one translation unit (capi_gemm.cu); everybody else calls run_gemm() declared in host.cuh.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include "host.cuh"
 
@@ -103,7 +104,19 @@ int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t stream) {
   memset(&args, 0, sizeof(args));
   args.M = p.M;
   args.N = p.N;
+  args.m_dev = p.m_dev;
+  args.k_dev = p.k_dev;
   args.nseg = p.nseg;
+  if (p.k_dev != nullptr) {
+    SRG_CHECK(p.flags & FLAG_BK_A, "gemm: device-resident K needs B to follow A's K coordinate");
+    for (int s = 1; s < p.nseg; ++s)
+      SRG_CHECK(p.seg[s].k_len == p.seg[0].k_len, "gemm: device-resident K needs equally long segments");
+  }
+  if (p.flags & FLAG_BK_A) {
+    SRG_CHECK(p.a_mn && p.b_mn, "gemm: FLAG_BK_A is for MN-major operands (weight gradients)");
+    for (int s = 0; s < p.nseg; ++s)
+      SRG_CHECK(p.seg[s].a.ptr == p.seg[0].a.ptr, "gemm: FLAG_BK_A needs every segment in the same A matrix");
+  }
 
   // A segments: distinct matrices share a descriptor slot
   const void* aptr[kMaxAMaps];
@@ -157,6 +170,12 @@ int run_gemm(const GemmProblem& p, const DeviceInfo& dev, cudaStream_t stream) {
               (long long)p.b.rows, (long long)p.b.cols, p.N, ktot);
     SRG_CHECK(ktot % kBlockK == 0 || p.b.cols == ktot, "gemm: K tail needs B cols == K");
     SRG_TRY(make_tmap(&maps.b, p.b.ptr, DT_BF16, p.N, ktot, p.b.ld, block_n / p.cg, kBlockK));
+  } else if (p.flags & FLAG_BK_A) {
+    int64_t kmax = 0;
+    for (int s = 0; s < p.nseg; ++s) kmax = std::max<int64_t>(kmax, p.seg[s].k_off + p.seg[s].k_len);
+    SRG_CHECK(p.b.rows >= kmax && p.b.cols >= p.N, "gemm: MN-major B [%lld,%lld] smaller than [K=%lld,N=%d]",
+              (long long)p.b.rows, (long long)p.b.cols, (long long)kmax, p.N);
+    SRG_TRY(make_tmap(&maps.b, p.b.ptr, DT_BF16, p.b.rows, p.N, p.b.ld, kBlockK, 64));
   } else {
     SRG_CHECK(p.b.rows >= ktot && p.b.cols >= p.N, "gemm: MN-major B [%lld,%lld] smaller than [K=%d,N=%d]",
               (long long)p.b.rows, (long long)p.b.cols, ktot, p.N);

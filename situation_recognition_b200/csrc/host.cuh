@@ -154,6 +154,10 @@ struct GemmProblem {
   int epi = EPI_STORE_F32;
   bool f32 = false;     // fp32-parity arithmetic in the epilogue
   int M = 0, N = 0;     // N multiple of the column tile
+  // device-resident sizes (see GemmArgs): with m_dev, M is the upper bound the operands are allocated for; with k_dev
+  // every segment's k_len is the upper bound of its device-resident length
+  const int* m_dev = nullptr;
+  const int* k_dev = nullptr;
   int nseg = 0;
   GemmSeg seg[kMaxSeg];
   Mat b;                // K-major: [N, Ktot]; MN-major: [Ktot, N]

@@ -68,36 +68,6 @@ __global__ void k_gather_mask(const int32_t* __restrict__ verb2roles, const int3
 }
 
 // ------------------------------------------------------------------------------------------------ node init
-__global__ void k_node_init_noun(const float* __restrict__ feat, const float* __restrict__ role_emb,
-                                 const float* __restrict__ verb_emb, const int64_t* __restrict__ verb,
-                                 const int32_t* __restrict__ verb2roles, int n_verbs, int B, int R, int D,
-                                 float* __restrict__ h32, bf16* __restrict__ hb_hi, Parts hb_lo) {
-  const int D4 = D / 4;
-  const int64_t total = static_cast<int64_t>(B) * D4;
-  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(t / D4);
-    const int d = static_cast<int>(t % D4) * 4;
-    int64_t v = verb[b];
-    if (v < 0 || v >= n_verbs) v = 0;
-    const float4 f = *reinterpret_cast<const float4*>(feat + static_cast<int64_t>(b) * D + d);
-    const float4 ve = *reinterpret_cast<const float4*>(verb_emb + v * D + d);
-    for (int r = 0; r < R; ++r) {
-      const int idx = verb2roles[v * R + r];
-      const float4 re = *reinterpret_cast<const float4*>(role_emb + static_cast<int64_t>(idx) * D + d);
-      float4 o;
-      // same association as the reference: (img_features * role_embd) * verb_embed_expand
-      o.x = fmaxf((f.x * re.x) * ve.x, 0.f);
-      o.y = fmaxf((f.y * re.y) * ve.y, 0.f);
-      o.z = fmaxf((f.z * re.z) * ve.z, 0.f);
-      o.w = fmaxf((f.w * re.w) * ve.w, 0.f);
-      const int64_t off = (static_cast<int64_t>(b) * R + r) * D + d;
-      *reinterpret_cast<float4*>(h32 + off) = o;
-      store4_split(hb_hi, hb_lo, off, o);
-    }
-  }
-}
-
 __global__ void k_node_init_verb(const float* __restrict__ feat, int64_t n4, float* __restrict__ h32,
                                  bf16* __restrict__ hb_hi, Parts hb_lo) {
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
@@ -149,6 +119,291 @@ __global__ void k_aggregate(const float* __restrict__ h32, const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------ compact role-node rows
+// Row layout of a role-graph path (RowMap, elementwise.cuh).  Image b owns rows [off[b], off[b] + L_b), L_b = its number
+// of real roles n_b (compact) or R (one row per slot); ONE shared pad row follows at meta[1] = sum L_b.  Pad nodes start
+// at 0 and only see themselves (model.py:95-97, imsitu_encoder.py:223-225), so every pad node of a batch follows the same
+// trajectory, which only depends on the weights: it is computed once.  Rows [meta[1], meta[2]) -- the shared pad row and
+// the rest of its 256-row GEMM tile -- are "self-loop rows": zero initial state, aggregate = own state.
+__global__ void __launch_bounds__(1024)
+k_prep_rows(const int32_t* __restrict__ role_count, int n_verbs, int R, const int64_t* __restrict__ verb, int B,
+            int compact, int* __restrict__ cnt, int* __restrict__ off, int* __restrict__ meta, int* __restrict__ bad) {
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (B + 1023) / 1024;
+  const int b0 = min(B, tid * per), b1 = min(B, b0 + per);
+  int sum = 0;
+  for (int b = b0; b < b1; ++b) {
+    int64_t v = verb[b];
+    if (v < 0 || v >= n_verbs) {
+      if (bad != nullptr) *bad = 1;
+      v = 0;
+    }
+    const int n = role_count[v];
+    cnt[b] = n;
+    sum += compact ? n : R;
+  }
+  s_part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {   // inclusive scan of the per-thread partial sums
+    const int v = (tid >= o) ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - sum;
+  for (int b = b0; b < b1; ++b) {
+    off[b] = run;
+    run += compact ? cnt[b] : R;
+  }
+  if (tid == 1023) {
+    const int n_real = s_part[1023];
+    off[B] = n_real;
+    meta[0] = n_real + 1;                        // rows, shared pad row included (the GEMMs' M)
+    meta[1] = n_real;                            // index of the shared pad row
+    meta[2] = (n_real + 1 + 255) / 256 * 256;    // rows the GEMM tiles touch (all of them hold finite values)
+    meta[3] = 0;
+  }
+}
+
+constexpr int kSelfRows = 256;   // upper bound of meta[2] - meta[1]
+
+__device__ __forceinline__ void store8_split(bf16* hi, Parts parts, int64_t idx, float4 a, float4 b) {
+  store4_split(hi, parts, idx, a);
+  store4_split(hi, parts, idx + 4, b);
+}
+
+__global__ void k_node_init_noun(const float* __restrict__ feat, const float* __restrict__ role_emb,
+                                 const float* __restrict__ verb_emb, const int64_t* __restrict__ verb,
+                                 const int32_t* __restrict__ verb2roles, int n_verbs, int B, int R, int D, RowMap rm,
+                                 float* __restrict__ h32, bf16* __restrict__ hb_hi, Parts hb_lo) {
+  const int D4 = D / 4;
+  const int64_t total = static_cast<int64_t>(B + kSelfRows) * D4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(t / D4);
+    const int d = static_cast<int>(t % D4) * 4;
+    if (u >= B) {   // self-loop rows start at exactly 0 (nn.Embedding padding_idx row)
+      const int row = rm.meta[1] + (u - B);
+      if (row < rm.meta[2]) {
+        const int64_t off = static_cast<int64_t>(row) * D + d;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(h32 + off) = z;
+        store4_split(hb_hi, hb_lo, off, z);
+      }
+      continue;
+    }
+    const int b = u;
+    int64_t v = verb[b];
+    if (v < 0 || v >= n_verbs) v = 0;
+    const float4 f = *reinterpret_cast<const float4*>(feat + static_cast<int64_t>(b) * D + d);
+    const float4 ve = *reinterpret_cast<const float4*>(verb_emb + v * D + d);
+    const int L = rm.compact ? rm.cnt[b] : R;
+    const int base = rm.off[b];
+    for (int r = 0; r < L; ++r) {
+      const int idx = verb2roles[v * R + r];
+      const float4 re = *reinterpret_cast<const float4*>(role_emb + static_cast<int64_t>(idx) * D + d);
+      float4 o;
+      // same association as the reference: (img_features * role_embd) * verb_embed_expand
+      o.x = fmaxf((f.x * re.x) * ve.x, 0.f);
+      o.y = fmaxf((f.y * re.y) * ve.y, 0.f);
+      o.z = fmaxf((f.z * re.z) * ve.z, 0.f);
+      o.w = fmaxf((f.w * re.w) * ve.w, 0.f);
+      const int64_t off = (static_cast<int64_t>(base) + r) * D + d;
+      *reinterpret_cast<float4*>(h32 + off) = o;
+      store4_split(hb_hi, hb_lo, off, o);
+    }
+  }
+}
+
+// a[i] = sum_{j < n, j != i} h[j] for the real nodes of an image (the closed form of the [R,R] mask of
+// imsitu_encoder.py:209-229 applied as in model.py:67-75, summed in the same order); a = h on pad / self-loop rows.
+__global__ void k_aggregate_rows(const float* __restrict__ h32, RowMap rm, int B, int R, int D, bf16* __restrict__ a_hi,
+                                 Parts a_lo) {
+  const int D4 = D / 4;
+  const int64_t total = static_cast<int64_t>(B + kSelfRows) * D4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(t / D4);
+    const int d = static_cast<int>(t % D4) * 4;
+    if (u >= B) {
+      const int row = rm.meta[1] + (u - B);
+      if (row < rm.meta[2]) {
+        const int64_t off = static_cast<int64_t>(row) * D + d;
+        store4_split(a_hi, a_lo, off, *reinterpret_cast<const float4*>(h32 + off));
+      }
+      continue;
+    }
+    const int n = rm.cnt[u];
+    const int L = rm.compact ? n : R;
+    const int64_t base = static_cast<int64_t>(rm.off[u]) * D + d;
+    float4 h[kMaxR];
+#pragma unroll
+    for (int j = 0; j < kMaxR; ++j)
+      if (j < L) h[j] = *reinterpret_cast<const float4*>(h32 + base + static_cast<int64_t>(j) * D);
+#pragma unroll
+    for (int i = 0; i < kMaxR; ++i) {
+      if (i < L) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+#pragma unroll
+          for (int j = 0; j < kMaxR; ++j) {
+            if (j < n && j != i) {
+              a.x += h[j].x; a.y += h[j].y; a.z += h[j].z; a.w += h[j].w;
+            }
+          }
+        } else {
+          a = h[i];
+        }
+        store4_split(a_hi, a_lo, base + static_cast<int64_t>(i) * D, a);
+      }
+    }
+  }
+}
+
+// ---- dropout: explicit keep-mask (tests) or counter-based Philox4x32-10 keyed by (seed, path stream, row, column / 8),
+// so the forward and the backward pass regenerate the same Bernoulli(1 - p) keep decisions without storing a mask
+// (model.py:106,110: nn.Dropout(0.5) in front of both classifiers).  One Philox block = 8 x 16 random bits = the keep
+// decisions of 8 consecutive columns: keep_i = (u16_i < (1 - p) * 65536).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// bit i of the result = keep column (8 * col8 + i) of `row`
+__device__ __forceinline__ uint32_t keep_bits8(const DropSpec& ds, int64_t row, int col8, int64_t ld_keep) {
+  if (ds.keep != nullptr) {
+    const uint2 k = *reinterpret_cast<const uint2*>(ds.keep + row * ld_keep + static_cast<int64_t>(col8) * 8);
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      m |= (((k.x >> (8 * i)) & 0xFFu) ? 1u : 0u) << i;
+      m |= (((k.y >> (8 * i)) & 0xFFu) ? 1u : 0u) << (4 + i);
+    }
+    return m;
+  }
+  if (ds.seed == nullptr) return 0xFFu;
+  const unsigned long long seed = static_cast<unsigned long long>(*ds.seed);
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>(col8),
+                                           static_cast<uint32_t>(ds.stream), static_cast<uint32_t>(row >> 32)),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m |= ((w[i] & 0xFFFFu) < ds.thresh ? 1u : 0u) << (2 * i);
+    m |= ((w[i] >> 16) < ds.thresh ? 1u : 0u) << (2 * i + 1);
+  }
+  return m;
+}
+
+__global__ void k_dropout_mask(DropSpec ds, int64_t rows, int D, uint8_t* __restrict__ out) {
+  const int D8 = D / 8;
+  const int64_t total = rows * D8;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = t / D8;
+    const int c8 = static_cast<int>(t % D8);
+    const uint32_t m = keep_bits8(ds, row, c8, D);
+    uint2 o;
+    o.x = (m & 1u) | ((m >> 1 & 1u) << 8) | ((m >> 2 & 1u) << 16) | ((m >> 3 & 1u) << 24);
+    o.y = (m >> 4 & 1u) | ((m >> 5 & 1u) << 8) | ((m >> 6 & 1u) << 16) | ((m >> 7 & 1u) << 24);
+    *reinterpret_cast<uint2*>(out + row * D + static_cast<int64_t>(c8) * 8) = o;
+  }
+}
+
+// Classifier input: x[row, :] = dropout(h[src(row), :]) as bf16 operand parts, for ALL B*R node slots (the dropout mask
+// differs per slot, so the classifier runs on every slot even though the pad slots share one state row).
+// rm.cnt == nullptr: src(row) = row (verb node path).
+__global__ void k_classifier_input(const float* __restrict__ h32, RowMap rm, int R, int64_t rows, int D, DropSpec ds,
+                                   bf16* __restrict__ x_hi, Parts x_lo) {
+  const int D8 = D / 8;
+  const int64_t total = rows * D8;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = t / D8;
+    const int c8 = static_cast<int>(t % D8);
+    int64_t src = row;
+    if (rm.cnt != nullptr) {
+      const int b = static_cast<int>(row / R), r = static_cast<int>(row % R);
+      const int L = rm.compact ? rm.cnt[b] : R;
+      src = (r < L) ? rm.off[b] + r : rm.meta[1];
+    }
+    const float* hp = h32 + src * D + c8 * 8;
+    float4 a = *reinterpret_cast<const float4*>(hp), b4 = *reinterpret_cast<const float4*>(hp + 4);
+    const uint32_t m = keep_bits8(ds, row, c8, D);
+    const float sc = ds.scale;
+    a.x = (m & 1u) ? a.x * sc : 0.f;
+    a.y = (m & 2u) ? a.y * sc : 0.f;
+    a.z = (m & 4u) ? a.z * sc : 0.f;
+    a.w = (m & 8u) ? a.w * sc : 0.f;
+    b4.x = (m & 16u) ? b4.x * sc : 0.f;
+    b4.y = (m & 32u) ? b4.y * sc : 0.f;
+    b4.z = (m & 64u) ? b4.z * sc : 0.f;
+    b4.w = (m & 128u) ? b4.w * sc : 0.f;
+    store8_split(x_hi, x_lo, row * D + c8 * 8, a, b4);
+  }
+}
+
+__global__ void k_zero_self_rows(float* __restrict__ x, RowMap rm, int D) {
+  const int D4 = D / 4;
+  const int64_t total = static_cast<int64_t>(kSelfRows) * D4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int row = rm.meta[1] + static_cast<int>(t / D4);
+    if (row < rm.meta[2])
+      *reinterpret_cast<float4*>(x + static_cast<int64_t>(row) * D + static_cast<int>(t % D4) * 4) =
+          make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// Backward of k_classifier_input: dh[dst(row), :] = dx[row, :] * keep * scale; the rows of all pad slots are SUMMED into
+// the shared pad row (the backward pass of one state row feeding many classifier rows), which k_zero_self_rows cleared.
+// grid = (column chunks, image slabs); rm.cnt == nullptr: one row per "image", R = 1 (verb node path).
+__global__ void k_classifier_input_bwd(const float* __restrict__ dx, RowMap rm, int B, int R, int D, DropSpec ds,
+                                       float* __restrict__ dh) {
+  const int D8 = D / 8;
+  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c8 >= D8) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  bool any_pad = false;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const int L = (rm.cnt != nullptr) ? (rm.compact ? rm.cnt[b] : R) : R;
+    const int64_t base = (rm.off != nullptr) ? rm.off[b] : static_cast<int64_t>(b) * R;
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = static_cast<int64_t>(b) * R + r;
+      const float* xp = dx + row * D + c8 * 8;
+      const float4 a = *reinterpret_cast<const float4*>(xp), b4 = *reinterpret_cast<const float4*>(xp + 4);
+      const uint32_t m = keep_bits8(ds, row, c8, D);
+      const float sc = ds.scale;
+      float v[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ((m >> i) & 1u) ? v[i] * sc : 0.f;
+      if (r < L) {
+        float* dp = dh + (base + r) * D + c8 * 8;
+        *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        any_pad = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+    }
+  }
+  if (any_pad) {
+    float* dp = dh + static_cast<int64_t>(rm.meta[1]) * D + c8 * 8;
+    atomicAdd(reinterpret_cast<float4*>(dp), make_float4(acc[0], acc[1], acc[2], acc[3]));
+    atomicAdd(reinterpret_cast<float4*>(dp + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ packing
 struct PackJobs {
   PackJob j[kMaxPackJobs];
@@ -178,37 +433,6 @@ __global__ void k_pack_bias(const float* __restrict__ a, const float* __restrict
     float v = 0.f;
     if (i < n) v = a[i] + (b != nullptr ? b[i] : 0.f);
     dst[i] = v;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ dropout
-__global__ void k_dropout_cast(const float* __restrict__ h32, const uint8_t* __restrict__ keep, float scale,
-                               int64_t n4, bf16* __restrict__ hi, Parts lo) {
-  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float4 f = *reinterpret_cast<const float4*>(h32 + t * 4);
-    const uchar4 k = *reinterpret_cast<const uchar4*>(keep + t * 4);
-    f.x = k.x ? f.x * scale : 0.f;
-    f.y = k.y ? f.y * scale : 0.f;
-    f.z = k.z ? f.z * scale : 0.f;
-    f.w = k.w ? f.w * scale : 0.f;
-    store4_split(hi, lo, t * 4, f);
-  }
-}
-
-__global__ void k_dropout_bwd(const float* __restrict__ dx, const uint8_t* __restrict__ keep, float scale, int64_t n4,
-                              float* __restrict__ dh) {
-  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n4;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float4 f = *reinterpret_cast<const float4*>(dx + t * 4);
-    if (keep != nullptr) {
-      const uchar4 k = *reinterpret_cast<const uchar4*>(keep + t * 4);
-      f.x = k.x ? f.x * scale : 0.f;
-      f.y = k.y ? f.y * scale : 0.f;
-      f.z = k.z ? f.z * scale : 0.f;
-      f.w = k.w ? f.w * scale : 0.f;
-    }
-    *reinterpret_cast<float4*>(dh + t * 4) = f;
   }
 }
 
@@ -415,7 +639,7 @@ __global__ void k_node_init_bwd(const float* __restrict__ dh0, const bf16* __res
                                 const float* __restrict__ feat, const float* __restrict__ role_emb,
                                 const float* __restrict__ verb_emb, const int64_t* __restrict__ verb,
                                 const int32_t* __restrict__ verb2roles, int n_verbs, int n_roles, int B, int R,
-                                int D, float* __restrict__ d_role_emb, float* __restrict__ d_verb_emb) {
+                                int D, RowMap rm, float* __restrict__ d_role_emb, float* __restrict__ d_verb_emb) {
   const int D4 = D / 4;
   const int64_t total = static_cast<int64_t>(B) * D4;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
@@ -427,10 +651,12 @@ __global__ void k_node_init_bwd(const float* __restrict__ dh0, const bf16* __res
     const float4 f = *reinterpret_cast<const float4*>(feat + static_cast<int64_t>(b) * D + d);
     const float4 ve = *reinterpret_cast<const float4*>(verb_emb + v * D + d);
     float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < R; ++r) {
+    const int n = rm.cnt[b];
+    const int64_t base = rm.off[b];
+    for (int r = 0; r < n; ++r) {
       const int idx = verb2roles[v * R + r];
       if (idx == n_roles) continue;  // padding_idx row: never receives a gradient, contributes 0 to verb_emb
-      const int64_t off = (static_cast<int64_t>(b) * R + r) * D + d;
+      const int64_t off = (base + r) * D + d;
       float4 g = *reinterpret_cast<const float4*>(dh0 + off);
       const uint2 hb = *reinterpret_cast<const uint2*>(h0b + off);
       g.x = (bf16_lo_f(hb.x) > 0.f) ? g.x : 0.f;
@@ -438,7 +664,7 @@ __global__ void k_node_init_bwd(const float* __restrict__ dh0, const bf16* __res
       g.z = (bf16_lo_f(hb.y) > 0.f) ? g.z : 0.f;
       g.w = (bf16_hi_f(hb.y) > 0.f) ? g.w : 0.f;
       const float4 re = *reinterpret_cast<const float4*>(role_emb + static_cast<int64_t>(idx) * D + d);
-      // ~190 embedding rows receive the gradients of B*R node rows: one 16-byte reduction per thread instead of four
+      // ~190 embedding rows receive the gradients of all node rows: one 16-byte reduction per thread instead of four
       atomicAdd(reinterpret_cast<float4*>(d_role_emb + static_cast<int64_t>(idx) * D + d),
                 make_float4(g.x * f.x * ve.x, g.y * f.y * ve.y, g.z * f.z * ve.z, g.w * f.w * ve.w));
       accv.x = fmaf(g.x * f.x, re.x, accv.x);
@@ -450,42 +676,57 @@ __global__ void k_node_init_bwd(const float* __restrict__ dh0, const bf16* __res
   }
 }
 
+// ada[j] = e[j] + sum_{i < n, i != j} da[i] on the real nodes of an image (the aggregation is symmetric, so its backward
+// pass is the same closed form), ada = e + da on pad / self-loop rows.  rm.cnt == nullptr: every one of the B rows is a
+// self-loop row (verb node path: the aggregation is the identity).  bf16 in / bf16 out, 8 columns per thread.
 __global__ void __launch_bounds__(kThreads, 4)
-k_aggregate_t_bf16(const bf16* __restrict__ dm, const float* __restrict__ mask, const bf16* __restrict__ add, int B,
-                   int R, int D, bf16* __restrict__ adm) {
+k_aggregate_t_rows(const bf16* __restrict__ da, const bf16* __restrict__ e, RowMap rm, int B, int R, int D,
+                   bf16* __restrict__ ada) {
   const int D8 = D / 8;
-  const int64_t total = static_cast<int64_t>(B) * D8;
+  const bool rows_only = (rm.cnt == nullptr);
+  const int64_t total = static_cast<int64_t>(rows_only ? B : B + kSelfRows) * D8;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(t / D8);
+    const int u = static_cast<int>(t / D8);
     const int d = static_cast<int>(t % D8) * 8;
-    // the six input rows stay packed as bf16 pairs and are widened where they are used -- as 48 floats they cost 112
-    // registers per thread, which left room for only two blocks per SM (2.6 TB/s)
+    int n = 0, L = 1;
+    int64_t base;
+    if (rows_only) {
+      base = static_cast<int64_t>(u) * D + d;
+    } else if (u >= B) {
+      const int row = rm.meta[1] + (u - B);
+      if (row >= rm.meta[2]) continue;
+      base = static_cast<int64_t>(row) * D + d;
+    } else {
+      n = rm.cnt[u];
+      L = rm.compact ? n : R;
+      base = static_cast<int64_t>(rm.off[u]) * D + d;
+    }
+    // the input rows stay packed as bf16 pairs and are widened where they are used (register pressure)
     uint4 g[kMaxR];
 #pragma unroll
     for (int i = 0; i < kMaxR; ++i)
-      if (i < R) g[i] = *reinterpret_cast<const uint4*>(dm + (static_cast<int64_t>(b) * R + i) * D + d);
-    const float* mb = (mask != nullptr) ? mask + static_cast<int64_t>(b) * R * R : nullptr;
+      if (i < L) g[i] = *reinterpret_cast<const uint4*>(da + base + static_cast<int64_t>(i) * D);
 #pragma unroll
     for (int j = 0; j < kMaxR; ++j) {
-      if (j < R) {
-        const uint4 ad = *reinterpret_cast<const uint4*>(add + (static_cast<int64_t>(b) * R + j) * D + d);
+      if (j < L) {
+        const uint4 ad = *reinterpret_cast<const uint4*>(e + base + static_cast<int64_t>(j) * D);
         float a[8] = {bf16_lo_f(ad.x), bf16_hi_f(ad.x), bf16_lo_f(ad.y), bf16_hi_f(ad.y),
                       bf16_lo_f(ad.z), bf16_hi_f(ad.z), bf16_lo_f(ad.w), bf16_hi_f(ad.w)};
 #pragma unroll
         for (int i = 0; i < kMaxR; ++i) {
-          if (i < R) {
-            const float m = (mb != nullptr) ? __ldg(mb + i * R + j) : 1.0f;
-            a[0] = fmaf(m, bf16_lo_f(g[i].x), a[0]); a[1] = fmaf(m, bf16_hi_f(g[i].x), a[1]);
-            a[2] = fmaf(m, bf16_lo_f(g[i].y), a[2]); a[3] = fmaf(m, bf16_hi_f(g[i].y), a[3]);
-            a[4] = fmaf(m, bf16_lo_f(g[i].z), a[4]); a[5] = fmaf(m, bf16_hi_f(g[i].z), a[5]);
-            a[6] = fmaf(m, bf16_lo_f(g[i].w), a[6]); a[7] = fmaf(m, bf16_hi_f(g[i].w), a[7]);
+          const bool on = (j < n) ? (i < n && i != j) : (i == j);
+          if (i < L && on) {
+            a[0] += bf16_lo_f(g[i].x); a[1] += bf16_hi_f(g[i].x);
+            a[2] += bf16_lo_f(g[i].y); a[3] += bf16_hi_f(g[i].y);
+            a[4] += bf16_lo_f(g[i].z); a[5] += bf16_hi_f(g[i].z);
+            a[6] += bf16_lo_f(g[i].w); a[7] += bf16_hi_f(g[i].w);
           }
         }
         uint4 o;
         const uint2 lo = pack4_bf16(a[0], a[1], a[2], a[3]), hi = pack4_bf16(a[4], a[5], a[6], a[7]);
         o.x = lo.x; o.y = lo.y; o.z = hi.x; o.w = hi.y;
-        *reinterpret_cast<uint4*>(adm + (static_cast<int64_t>(b) * R + j) * D + d) = o;
+        *reinterpret_cast<uint4*>(ada + base + static_cast<int64_t>(j) * D) = o;
       }
     }
   }
@@ -494,14 +735,20 @@ k_aggregate_t_bf16(const bf16* __restrict__ dm, const float* __restrict__ mask, 
 struct ColsumJobs {
   ColsumJob j[4];
 };
-// grid = (column chunks of 64, row slabs, jobs)
-__global__ void k_colsum_multi(ColsumJobs jobs, int64_t ld, int rows, int n_cols) {
+// grid = (column chunks of 64, segments * row slabs, jobs).  The rows are nseg segments of `rows` rows each (rows_dev, when
+// given, holds the number of valid rows per segment), segment s starting at row s * seg_stride of X.
+__global__ void k_colsum_multi(ColsumJobs jobs, int64_t ld, int rows, const int* __restrict__ rows_dev, int nseg,
+                               int64_t seg_stride, int n_cols) {
   __shared__ float2 red[8][32];
-  const ColsumJob job = jobs.j[blockIdx.z];
+  ColsumJob job = jobs.j[blockIdx.z];
+  if (rows_dev != nullptr) rows = __ldg(rows_dev);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + lane * 2;
-  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
-  const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  const int slabs = gridDim.y / nseg;
+  const int seg = blockIdx.y / slabs, slab = blockIdx.y % slabs;
+  job.X += static_cast<int64_t>(seg) * seg_stride * ld;
+  const int rows_per = (rows + slabs - 1) / slabs;
+  const int r0 = slab * rows_per, r1 = min(rows, r0 + rows_per);
   float2 acc = make_float2(0.f, 0.f);
   if (c < n_cols) {
     int r = r0 + w;
@@ -546,8 +793,10 @@ __global__ void k_colsum_multi(ColsumJobs jobs, int64_t ld, int rows, int n_cols
 }
 
 __global__ void k_gru_bwd_pre_ld(const float* __restrict__ dh, const bf16* __restrict__ z, const bf16* __restrict__ hc,
-                                 const bf16* __restrict__ h, int rows, int D, bf16* __restrict__ dpre_z,
-                                 bf16* __restrict__ dpre_h, int64_t ld_out, float* __restrict__ dh_acc) {
+                                 const bf16* __restrict__ h, int rows, const int* __restrict__ rows_dev, int D,
+                                 bf16* __restrict__ dpre_z, bf16* __restrict__ dpre_h, int64_t ld_out,
+                                 float* __restrict__ dh_acc) {
+  if (rows_dev != nullptr) rows = __ldg(rows_dev);
   const int D4 = D / 4;
   const int64_t total = static_cast<int64_t>(rows) * D4;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
@@ -722,16 +971,6 @@ int launch_gather_mask(const int32_t* verb2roles, const int32_t* role_count, int
   return SRG_OK;
 }
 
-int launch_node_init_noun(const float* feat, const float* role_emb, const float* verb_emb, const int64_t* verb,
-                          const int32_t* verb2roles, int n_verbs, int B, int R, int D, float* h32, bf16* hb_hi,
-                          bf16* hb_mid, bf16* hb_lo, cudaStream_t s) {
-  if (B <= 0) return SRG_OK;
-  k_node_init_noun<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(
-      feat, role_emb, verb_emb, verb, verb2roles, n_verbs, B, R, D, h32, hb_hi, Parts{hb_mid, hb_lo});
-  SRG_LAUNCH_CHECK();
-  return SRG_OK;
-}
-
 int launch_node_init_verb(const float* feat, int B, int D, float* h32, bf16* hb_hi, bf16* hb_mid, bf16* hb_lo,
                           cudaStream_t s) {
   if (B <= 0) return SRG_OK;
@@ -772,21 +1011,6 @@ int launch_pack_weight_multi(const PackJob* jobs, int n_jobs, int cols, cudaStre
 
 int launch_pack_bias(const float* a, const float* b, int n, int n_pad, float* dst, cudaStream_t s) {
   k_pack_bias<<<grid_for(n_pad), kThreads, 0, s>>>(a, b, n, n_pad, dst);
-  SRG_LAUNCH_CHECK();
-  return SRG_OK;
-}
-
-int launch_dropout_cast(const float* h32, const uint8_t* keep, float scale, int64_t n, bf16* hi, bf16* mid, bf16* lo,
-                        cudaStream_t s) {
-  if (n <= 0) return SRG_OK;
-  k_dropout_cast<<<grid_for(n / 4), kThreads, 0, s>>>(h32, keep, scale, n / 4, hi, Parts{mid, lo});
-  SRG_LAUNCH_CHECK();
-  return SRG_OK;
-}
-
-int launch_dropout_bwd(const float* dx, const uint8_t* keep, float scale, int64_t n, float* dh, cudaStream_t s) {
-  if (n <= 0) return SRG_OK;
-  k_dropout_bwd<<<grid_for(n / 4), kThreads, 0, s>>>(dx, keep, scale, n / 4, dh);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
@@ -848,43 +1072,113 @@ int launch_colsum(const bf16* X, int64_t ld, int rows, int n_cols, float* out1, 
   return SRG_OK;
 }
 
-int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, const float* role_emb,
-                         const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_verbs,
-                         int n_roles, int B, int R, int D, float* d_role_emb, float* d_verb_emb, cudaStream_t s) {
+int launch_prep_rows(const int32_t* role_count, int n_verbs, int R, const int64_t* verb, int B, int compact,
+                     RowMap rm, int* bad, cudaStream_t s) {
   if (B <= 0) return SRG_OK;
-  k_node_init_bwd<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(
-      dh0, h0b, feat, role_emb, verb_emb, verb, verb2roles, n_verbs, n_roles, B, R, D, d_role_emb, d_verb_emb);
+  k_prep_rows<<<1, 1024, 0, s>>>(role_count, n_verbs, R, verb, B, compact, const_cast<int*>(rm.cnt),
+                                 const_cast<int*>(rm.off), const_cast<int*>(rm.meta), bad);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
-int launch_aggregate_t_bf16(const bf16* dm, const float* mask, const bf16* add, int B, int R, int D, bf16* adm,
-                            cudaStream_t s) {
+int launch_node_init_noun(const float* feat, const float* role_emb, const float* verb_emb, const int64_t* verb,
+                          const int32_t* verb2roles, int n_verbs, int B, int R, int D, RowMap rm, float* h32,
+                          bf16* hb_hi, bf16* hb_mid, bf16* hb_lo, cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
-  k_aggregate_t_bf16<<<grid_for(static_cast<int64_t>(B) * D / 8), kThreads, 0, s>>>(dm, mask, add, B, R, D, adm);
+  k_node_init_noun<<<grid_for(static_cast<int64_t>(B + kSelfRows) * D / 4), kThreads, 0, s>>>(
+      feat, role_emb, verb_emb, verb, verb2roles, n_verbs, B, R, D, rm, h32, hb_hi, Parts{hb_mid, hb_lo});
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
-int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows, int n_cols, cudaStream_t s) {
-  if (rows <= 0 || n_cols <= 0 || n_jobs <= 0) return SRG_OK;
+int launch_aggregate_rows(const float* h32, RowMap rm, int B, int R, int D, bf16* a_hi, bf16* a_mid, bf16* a_lo,
+                          cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
+  k_aggregate_rows<<<grid_for(static_cast<int64_t>(B + kSelfRows) * D / 4), kThreads, 0, s>>>(h32, rm, B, R, D, a_hi,
+                                                                                            Parts{a_mid, a_lo});
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_aggregate_t_rows(const bf16* da, const bf16* e, RowMap rm, int B, int R, int D, bf16* ada, cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  if (R > kMaxR) return set_error(SRG_ERR_UNSUPPORTED, "max_role_count %d > %d", R, kMaxR);
+  const int64_t units = (rm.cnt == nullptr) ? B : B + kSelfRows;
+  k_aggregate_t_rows<<<grid_for(units * D / 8), kThreads, 0, s>>>(da, e, rm, B, R, D, ada);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_classifier_input(const float* h32, RowMap rm, int R, int64_t rows, int D, DropSpec ds, bf16* x_hi,
+                            bf16* x_mid, bf16* x_lo, cudaStream_t s) {
+  if (rows <= 0) return SRG_OK;
+  if (D % 8 != 0) return set_error(SRG_ERR_ARG, "classifier_input: D=%d must be a multiple of 8", D);
+  k_classifier_input<<<grid_for(rows * D / 8), kThreads, 0, s>>>(h32, rm, R, rows, D, ds, x_hi, Parts{x_mid, x_lo});
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_classifier_input_bwd(const float* dx, RowMap rm, int B, int R, int D, DropSpec ds, float* dh,
+                                cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  if (D % 8 != 0) return set_error(SRG_ERR_ARG, "classifier_input_bwd: D=%d must be a multiple of 8", D);
+  if (rm.meta != nullptr) {   // the shared pad row (and the rest of its tile) is accumulated into: clear it first
+    k_zero_self_rows<<<grid_for(static_cast<int64_t>(kSelfRows) * D / 4), kThreads, 0, s>>>(dh, rm, D);
+    SRG_LAUNCH_CHECK();
+  }
+  const int D8 = D / 8;
+  const int threads = D8 < kThreads ? D8 : kThreads;
+  const int chunks = (D8 + threads - 1) / threads;
+  int slabs = (148 * 8) / chunks;
+  if (slabs > B) slabs = B;
+  if (slabs < 1) slabs = 1;
+  dim3 grid(chunks, slabs);
+  k_classifier_input_bwd<<<grid, threads, 0, s>>>(dx, rm, B, R, D, ds, dh);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_dropout_mask(DropSpec ds, int64_t rows, int D, uint8_t* out, cudaStream_t s) {
+  if (rows <= 0) return SRG_OK;
+  if (D % 8 != 0) return set_error(SRG_ERR_ARG, "dropout_mask: D=%d must be a multiple of 8", D);
+  k_dropout_mask<<<grid_for(rows * D / 8), kThreads, 0, s>>>(ds, rows, D, out);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_node_init_bwd(const float* dh0, const bf16* h0b, const float* feat, const float* role_emb,
+                         const float* verb_emb, const int64_t* verb, const int32_t* verb2roles, int n_verbs,
+                         int n_roles, int B, int R, int D, RowMap rm, float* d_role_emb, float* d_verb_emb,
+                         cudaStream_t s) {
+  if (B <= 0) return SRG_OK;
+  k_node_init_bwd<<<grid_for(static_cast<int64_t>(B) * D / 4), kThreads, 0, s>>>(
+      dh0, h0b, feat, role_emb, verb_emb, verb, verb2roles, n_verbs, n_roles, B, R, D, rm, d_role_emb, d_verb_emb);
+  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows, const int* rows_dev, int nseg,
+                        int64_t seg_stride, int n_cols, cudaStream_t s) {
+  if (rows <= 0 || n_cols <= 0 || n_jobs <= 0 || nseg <= 0) return SRG_OK;
   if (n_jobs > 4) return set_error(SRG_ERR_ARG, "colsum_multi: at most 4 jobs");
   ColsumJobs js;
   for (int i = 0; i < 4; ++i) js.j[i] = jobs[i < n_jobs ? i : 0];
-  int slabs = (rows + 511) / 512;
-  if (slabs > 37) slabs = 37;
-  dim3 grid((n_cols + 63) / 64, slabs, n_jobs);
-  k_colsum_multi<<<grid, kThreads, 0, s>>>(js, ld, rows, n_cols);
+  int slabs = (rows + 511) / 512;                 // per segment
+  if (slabs * nseg > 40) slabs = 40 / nseg;
+  if (slabs < 1) slabs = 1;
+  dim3 grid((n_cols + 63) / 64, slabs * nseg, n_jobs);
+  k_colsum_multi<<<grid, kThreads, 0, s>>>(js, ld, rows, rows_dev, nseg, seg_stride, n_cols);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
-int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int rows, int D,
-                          bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc, cudaStream_t s) {
+int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int rows, const int* rows_dev,
+                          int D, bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc, cudaStream_t s) {
   if (rows <= 0) return SRG_OK;
-  k_gru_bwd_pre_ld<<<grid_for(static_cast<int64_t>(rows) * D / 4), kThreads, 0, s>>>(dh, z, hc, h, rows, D, dpre_z,
-                                                                                    dpre_h, ld_out, dh_acc);
+  k_gru_bwd_pre_ld<<<grid_for(static_cast<int64_t>(rows) * D / 4), kThreads, 0, s>>>(dh, z, hc, h, rows, rows_dev, D,
+                                                                                    dpre_z, dpre_h, ld_out, dh_acc);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }

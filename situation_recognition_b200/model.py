@@ -15,6 +15,7 @@ Differences a caller can observe (all documented in DESIGN.md):
     keep working without `nn.DataParallel`.
 """
 import ctypes
+import os
 import warnings
 
 import torch
@@ -25,6 +26,7 @@ from ._lib import SRG_MODE_NOUN, SRG_MODE_VERB, SRG_PREC_BF16, SRG_PREC_FP32
 from .imsitu_encoder import tables_from_encoder
 
 T_STEPS = 4  # model.py:60
+_POISON_WS = os.environ.get("SRG_POISON_WS", "0") == "1"
 
 
 def _pad256(n):
@@ -96,6 +98,10 @@ class _Engine:
 
     def set_cta_group(self, cg):
         _lib.check(self.lib.srg_set_cta_group(self.h, cg))
+
+    def set_compact_rows(self, on):
+        """Role-graph rows: real role nodes + one shared pad row (default) or the reference's R rows per image."""
+        _lib.check(self.lib.srg_set_compact_rows(self.h, int(bool(on))))
 
     def param_list(self, model):
         g = model.ggsnn
@@ -176,7 +182,10 @@ class _Engine:
 
     def workspace(self, mode, B, prec, save):
         n = self.lib.srg_workspace_bytes(self.h, mode, B, prec, int(save))
-        return torch.empty(n, dtype=torch.uint8, device=self.device)
+        ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+        if _POISON_WS:      # tests: every byte 0xFF = NaN as fp32 / bf16, -1 as int32: a read of a workspace location
+            ws.fill_(0xFF)  # nobody wrote shows up as NaN in the results instead of hiding behind fresh (zeroed) memory
+        return ws
 
 
 def _stats_view(eng, ws, mode, B, prec, save):
@@ -218,7 +227,7 @@ class _NounsStage(torch.autograd.Function):
     """predict_nouns minus the backbone (model.py:117-155)."""
 
     @staticmethod
-    def forward(ctx, model, grad_on, feat, verb, keep, role_emb, verb_emb, *params):
+    def forward(ctx, model, grad_on, feat, verb, keep, seed, slot, role_emb, verb_emb, *params):
         eng = model._engine_for(feat.device)
         prec = _prec_code(model.precision)
         B = feat.shape[0]
@@ -226,19 +235,20 @@ class _NounsStage(torch.autograd.Function):
         if need_grad and prec != SRG_PREC_BF16:
             raise _lib.SrgError("precision='fp32' is a forward-only parity mode; use torch.no_grad() or precision='bf16'")
         eng.ensure_packed(model, prec)
-        drop_p = model.drop_p if keep is not None else 0.0
+        drop_p = model.drop_p if (keep is not None or seed is not None) else 0.0
         logits = torch.empty(B * eng.R, eng.Lpad, dtype=torch.float32, device=feat.device)
         ws = eng.workspace(SRG_MODE_NOUN, B, prec, need_grad)
         verb = verb.detach().to(torch.int64).contiguous()
         _lib.check(eng.lib.srg_nouns_forward(eng.h, _lib.ptr(feat), _lib.ptr(verb), B, _lib.ptr(role_emb),
-                                             _lib.ptr(verb_emb), _lib.ptr(keep), drop_p, _lib.ptr(logits), eng.Lpad,
-                                             prec, int(need_grad), _lib.ptr(ws), ws.numel(), eng.stream()))
+                                             _lib.ptr(verb_emb), _lib.ptr(keep), drop_p, _lib.ptr(seed), slot,
+                                             _lib.ptr(logits), eng.Lpad, prec, int(need_grad), _lib.ptr(ws), ws.numel(),
+                                             eng.stream()))
         if need_grad:
-            ctx.eng, ctx.ws, ctx.B, ctx.drop_p = eng, ws, B, drop_p
+            ctx.eng, ctx.ws, ctx.B, ctx.drop_p, ctx.slot = eng, ws, B, drop_p, slot
             ctx.pack_gen = eng.pack_gen
             ctx.direct = model._direct_grads()
             ctx.live = (role_emb, verb_emb) + tuple(params)       # the Parameter objects (for .grad in direct mode)
-            ctx.save_for_backward(feat, verb, keep, role_emb, verb_emb, *params)
+            ctx.save_for_backward(feat, verb, keep, seed, role_emb, verb_emb, *params)
         model._last_stats = _stats_view(eng, ws, SRG_MODE_NOUN, B, prec, need_grad)
         return logits.view(B, eng.R, eng.Lpad)[:, :, :eng.L]
 
@@ -246,7 +256,7 @@ class _NounsStage(torch.autograd.Function):
     def backward(ctx, dlogits):
         eng = ctx.eng
         eng.check_pack_gen(ctx.pack_gen)
-        feat, verb, keep, role_emb, verb_emb, *params = ctx.saved_tensors
+        feat, verb, keep, seed, role_emb, verb_emb, *params = ctx.saved_tensors
         B = ctx.B
         dl, ldl = _padded_grad(dlogits.reshape(B * eng.R, eng.L), eng.Lpad)
         names = ["role_emb", "verb_emb"] + _GGNN_FIELDS + ["Wc_noun", "bc_noun"]
@@ -259,20 +269,21 @@ class _NounsStage(torch.autograd.Function):
         sg = _grad_struct(grads, eng)
         _lib.check(eng.lib.srg_nouns_backward(eng.h, _lib.ptr(dl), ldl, _lib.ptr(feat), _lib.ptr(verb), B,
                                               _lib.ptr(role_emb), _lib.ptr(verb_emb), _lib.ptr(keep), ctx.drop_p,
-                                              ctypes.byref(sg), _lib.ptr(ctx.ws), ctx.ws.numel(), eng.stream()))
+                                              _lib.ptr(seed), ctx.slot, ctypes.byref(sg), _lib.ptr(ctx.ws),
+                                              ctx.ws.numel(), eng.stream()))
         ctx.ws = None
         if ctx.direct:
             eng.backward_mark()
-            return (None,) * (5 + len(names))
+            return (None,) * (7 + len(names))
         out = [grads[n] for n in _GGNN_FIELDS + ["Wc_noun", "bc_noun"]]
-        return (None, None, None, None, None, grads["role_emb"], grads["verb_emb"], *out)
+        return (None, None, None, None, None, None, None, grads["role_emb"], grads["verb_emb"], *out)
 
 
 class _VerbStage(torch.autograd.Function):
     """predict_verb minus the backbone (model.py:160-168)."""
 
     @staticmethod
-    def forward(ctx, model, grad_on, feat, keep, *params):
+    def forward(ctx, model, grad_on, feat, keep, seed, slot, *params):
         eng = model._engine_for(feat.device)
         prec = _prec_code(model.precision)
         B = feat.shape[0]
@@ -280,18 +291,18 @@ class _VerbStage(torch.autograd.Function):
         if need_grad and prec != SRG_PREC_BF16:
             raise _lib.SrgError("precision='fp32' is a forward-only parity mode; use torch.no_grad() or precision='bf16'")
         eng.ensure_packed(model, prec)
-        drop_p = model.drop_p if keep is not None else 0.0
+        drop_p = model.drop_p if (keep is not None or seed is not None) else 0.0
         logits = torch.empty(B, eng.Vpad, dtype=torch.float32, device=feat.device)
         ws = eng.workspace(SRG_MODE_VERB, B, prec, need_grad)
-        _lib.check(eng.lib.srg_verb_forward(eng.h, _lib.ptr(feat), B, _lib.ptr(keep), drop_p, _lib.ptr(logits),
-                                            eng.Vpad, prec, int(need_grad), _lib.ptr(ws), ws.numel(),
+        _lib.check(eng.lib.srg_verb_forward(eng.h, _lib.ptr(feat), B, _lib.ptr(keep), drop_p, _lib.ptr(seed), slot,
+                                            _lib.ptr(logits), eng.Vpad, prec, int(need_grad), _lib.ptr(ws), ws.numel(),
                                             eng.stream()))
         if need_grad:
-            ctx.eng, ctx.ws, ctx.B, ctx.drop_p = eng, ws, B, drop_p
+            ctx.eng, ctx.ws, ctx.B, ctx.drop_p, ctx.slot = eng, ws, B, drop_p, slot
             ctx.pack_gen = eng.pack_gen
             ctx.direct = model._direct_grads()
             ctx.live = tuple(params)
-            ctx.save_for_backward(keep, *params)
+            ctx.save_for_backward(keep, seed, *params)
         model._last_stats = _stats_view(eng, ws, SRG_MODE_VERB, B, prec, need_grad)
         return logits[:, :eng.V]
 
@@ -299,7 +310,7 @@ class _VerbStage(torch.autograd.Function):
     def backward(ctx, dlogits):
         eng = ctx.eng
         eng.check_pack_gen(ctx.pack_gen)
-        keep, *params = ctx.saved_tensors
+        keep, seed, *params = ctx.saved_tensors
         B = ctx.B
         dl, ldl = _padded_grad(dlogits.reshape(B, eng.V), eng.Vpad)
         names = _GGNN_FIELDS + ["Wc_verb", "bc_verb"]
@@ -310,13 +321,13 @@ class _VerbStage(torch.autograd.Function):
             grads = {n: torch.zeros_like(p) for n, p in zip(names, params)}
             eng.set_deferred(False)
         sg = _grad_struct(grads, eng)
-        _lib.check(eng.lib.srg_verb_backward(eng.h, _lib.ptr(dl), ldl, B, _lib.ptr(keep), ctx.drop_p, ctypes.byref(sg),
-                                             _lib.ptr(ctx.ws), ctx.ws.numel(), eng.stream()))
+        _lib.check(eng.lib.srg_verb_backward(eng.h, _lib.ptr(dl), ldl, B, _lib.ptr(keep), ctx.drop_p, _lib.ptr(seed),
+                                             ctx.slot, ctypes.byref(sg), _lib.ptr(ctx.ws), ctx.ws.numel(), eng.stream()))
         ctx.ws = None
         if ctx.direct:
             eng.backward_mark()
-            return (None,) * (4 + len(names))
-        return (None, None, None, None, *[grads[n] for n in names])
+            return (None,) * (6 + len(names))
+        return (None, None, None, None, None, None, *[grads[n] for n in names])
 
 
 def _padded_grad(g, npad):
@@ -479,6 +490,9 @@ class FCGGNN(nn.Module):
         self.global_batch = None        # images of the current GLOBAL batch when the caller knows it (saves the
                                         # all-reduce of the local batch sizes in verb_loss); None = all-reduce
         self.dropout_masks = None       # optional (verb, pred-noun, gt-noun) uint8 keep-masks for parity tests
+        self._seed_state = {}           # device -> int64[1] dropout seed counter (Philox key of the next forward)
+        self._step_seed = None          # seed shared by the three paths of the forward() call in flight
+        self.last_drop_seed = None      # seed tensor the most recent training forward used (tests replay its masks)
         self.role_emb = nn.Embedding(encoder.get_num_roles() + 1, D_hidden_state, padding_idx=encoder.get_num_roles())
         self.verb_emb = nn.Embedding(encoder.get_num_verbs(), D_hidden_state)
         if backbone == "resnet152":
@@ -525,13 +539,37 @@ class FCGGNN(nn.Module):
         return [g.W_p.weight, g.W_p.bias, g.W_z.weight, g.W_z.bias, g.U_z.weight, g.U_z.bias, g.W_r.weight, g.W_r.bias,
                 g.U_r.weight, g.U_r.bias, g.W_h.weight, g.W_h.bias, g.U_h.weight, g.U_h.bias]
 
-    def _keep_mask(self, which, rows, device):
+    def _draw_seed(self, device):
+        """A fresh dropout seed (device int64[1]) without a host synchronisation, so that it also works inside a CUDA
+        graph: the seed tensor handed out is a copy of a device counter that is then advanced.  The counter starts from
+        torch's CPU generator, so `torch.manual_seed` makes training runs repeatable."""
+        state = self._seed_state.get(device)
+        if state is None:
+            state = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(device)
+            self._seed_state[device] = state
+        seed = state.clone()
+        state.add_(1)
+        self.last_drop_seed = seed
+        return seed
+
+    def _dropout(self, which, device):
+        """(explicit keep-mask | None, Philox seed | None) for path `which` (0 verb, 1 predicted-verb nouns, 2 gt nouns).
+        Eval mode: (None, None).  model.py:106,110: nn.Dropout(0.5) in front of both classifiers."""
         if not self.training:
-            return None
+            return None, None
         if self.dropout_masks is not None:
             m = self.dropout_masks[which]
-            return None if m is None else m.to(device=device, dtype=torch.uint8).contiguous()
-        return torch.empty(rows, self.D, dtype=torch.uint8, device=device).bernoulli_(1.0 - self.drop_p)
+            return (None if m is None else m.to(device=device, dtype=torch.uint8).contiguous()), None
+        return None, (self._step_seed if self._step_seed is not None else self._draw_seed(device))
+
+    def dropout_mask(self, which, rows, seed=None):
+        """The uint8 keep-mask [rows, D] the Philox path applied (applies) on path `which` for `seed` (default: the
+        seed of the most recent training forward).  Test helper: lets the oracle replay a training step's dropout."""
+        seed = self.last_drop_seed if seed is None else seed
+        eng = self._engine_for(seed.device)
+        out = torch.empty(rows, self.D, dtype=torch.uint8, device=seed.device)
+        _lib.check(eng.lib.srg_dropout_mask(_lib.ptr(seed), which, self.drop_p, rows, self.D, _lib.ptr(out), eng.stream()))
+        return out
 
     # ---- reference API -------------------------------------------------------------------------
     def predict_nouns(self, img, gt_verb, batch_size, _mask_slot=1, _feat=None):
@@ -540,9 +578,9 @@ class FCGGNN(nn.Module):
         feat = _feat if _feat is not None else _as_feat(self.convnet_nouns(img), self.D)
         if feat.shape[0] != batch_size:
             raise _lib.SrgError("batch_size %d does not match the features (%d)" % (batch_size, feat.shape[0]))
-        keep = self._keep_mask(_mask_slot, batch_size * self.encoder.get_max_role_count(), feat.device)
+        keep, seed = self._dropout(_mask_slot, feat.device)
         gt_verb = gt_verb.to(feat.device)
-        out = _NounsStage.apply(self, torch.is_grad_enabled(), feat, gt_verb, keep, self.role_emb.weight,
+        out = _NounsStage.apply(self, torch.is_grad_enabled(), feat, gt_verb, keep, seed, _mask_slot, self.role_emb.weight,
                                 self.verb_emb.weight, *self._ggnn_params(), self.nouns_classifier[1].weight,
                                 self.nouns_classifier[1].bias)
         out._srg_stats = self._last_stats      # lets nouns_loss() reuse the classifier's per-tile softmax statistics
@@ -552,8 +590,8 @@ class FCGGNN(nn.Module):
         feat = _as_feat(self.convnet_verbs(img), self.D)
         if feat.shape[0] != batch_size:
             raise _lib.SrgError("batch_size %d does not match the features (%d)" % (batch_size, feat.shape[0]))
-        keep = self._keep_mask(0, batch_size, feat.device)
-        out = _VerbStage.apply(self, torch.is_grad_enabled(), feat, keep, *self._ggnn_params(),
+        keep, seed = self._dropout(0, feat.device)
+        out = _VerbStage.apply(self, torch.is_grad_enabled(), feat, keep, seed, 0, *self._ggnn_params(),
                                self.verb_classifier[1].weight, self.verb_classifier[1].bias)
         out._srg_stats = self._last_stats
         return out
@@ -567,6 +605,15 @@ class FCGGNN(nn.Module):
         waits for it.  autograd replays the same streams, so the two backward passes overlap as well."""
         batch_size = img.size(0)
         img_n = img if img_nouns is None else img_nouns
+        self._step_seed = None
+        if self.training and self.dropout_masks is None and img.is_cuda:
+            self._step_seed = self._draw_seed(img.device)       # one Philox key for the three paths of this step
+        try:
+            return self._forward_paths(img, img_n, gt_verb, batch_size)
+        finally:
+            self._step_seed = None
+
+    def _forward_paths(self, img, img_n, gt_verb, batch_size):
         # the noun backbone is frozen and deterministic in eval mode: evaluate it once for both noun passes
         feat_n = None
         if img_n.is_cuda and not (self.training and _has_batchnorm_in_train(self.convnet_nouns)):
@@ -630,6 +677,14 @@ class FCGGNN(nn.Module):
         _lib.check(eng.lib.srg_ggnn_forward(eng.h, mode, _lib.ptr(h), _lib.ptr(mk), B, prec, 0, _lib.ptr(ws),
                                             ws.numel(), eng.stream()))
         return h
+
+    def check_verbs(self, device=None):
+        """Raise SrgError if any predict_nouns / forward call since the last check saw a verb id outside
+        [0, num_verbs) (the kernels clamp such ids to 0 instead of faulting; the reference raises an IndexError).
+        Synchronises the stream: call it when debugging data, not in the training loop."""
+        for key, eng in self._engines.items():
+            if device is None or torch.device(device).index in (None, key[1]):
+                _lib.check(eng.lib.srg_check_verbs(eng.h, eng.stream()))
 
     def gather_mask(self, verbs):
         """CUDA replacement of encoder.get_role_ids_batch + get_adj_matrix_noself (imsitu_encoder.py:172-180,209-229)."""

@@ -9,6 +9,11 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The stage's workspaces come from torch's caching allocator uninitialised.  In the tests every workspace is filled with
+# 0xFF bytes (NaN as fp32 / bf16) first, so a kernel that reads a row nobody wrote fails a parity test instead of passing
+# on memory that happened to be zero.  Must be set before the package is imported.
+os.environ.setdefault("SRG_POISON_WS", "1")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) GPU; run with -m gpu on the GPU box")

@@ -108,6 +108,13 @@ def test_gather_mask_edge_cases(enc_syn, enc_over):
     assert role_idx.shape == (0, 6) and mask.shape == (0, 6, 6)
     _, _, bad = m.gather_mask(torch.tensor([3, 504], device="cuda"))
     assert int(bad.item()) == 1                                  # out-of-range verb id is flagged, not read
+    with torch.no_grad():                                          # the stage clamps a bad id, flags it, and check_verbs raises
+        m.eval()
+        m.predict_nouns(torch.rand(2, 256, device="cuda"), torch.tensor([3, 9999], device="cuda"), 2)
+        with pytest.raises(S._lib.SrgError):
+            m.check_verbs()
+        m.predict_nouns(torch.rand(2, 256, device="cuda"), torch.tensor([3, 4], device="cuda"), 2)
+        m.check_verbs()                                            # the flag was cleared; valid ids do not raise it
     g = golden("encoder_overfitting.npz")                          # R = 4 vocabulary of the reference's own fixture
     m4 = S.FCGGNN(enc_over, 256, backbone=None).cuda()
     role_idx, mask, _ = m4.gather_mask(torch.arange(5, device="cuda"))
@@ -289,6 +296,65 @@ def test_train_step_gradients_vs_oracle(enc_syn, B, flat):
         assert abs(mine.item() - float(ref)) <= 2e-3 * float(ref)
     for k, e in errs.items():
         assert e <= 3e-2, (k, e)
+
+
+def test_philox_dropout_step_vs_oracle(enc_syn):
+    """Training mode WITHOUT an explicit mask: the kernels draw the dropout keep decisions from Philox (seed on the
+    device, regenerated in backward).  srg_dropout_mask materialises the masks that seed implies; the oracle replays
+    the step with them.  Also: the masks are Bernoulli(0.5), differ between paths and change from step to step."""
+    B, D = 48, 2048
+    params = O.init_params(504, 190, 2001, D, seed=0)
+    fv, fn, gt_verb, gt_nouns = make_batch(enc_syn, B, D, seed=78)
+    t, c = O.build_tables(enc_syn.roles_per_verb, enc_syn.verb_list, enc_syn.role_list)
+    m = model_from(params, enc_syn, D, "bf16").train()
+    torch.manual_seed(123)
+    mpv, mpn, mgpn = m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())
+    seed = m.last_drop_seed
+    lv, ln, lg = m.verb_loss(mpv, gt_verb.cuda()), m.nouns_loss(mpn, gt_nouns.cuda()), m.nouns_loss(mgpn, gt_nouns.cuda())
+    (lv + ln).backward()
+    masks = [m.dropout_mask(w, r, seed) for w, r in ((0, B), (1, B * 6), (2, B * 6))]
+    for k in masks:
+        assert abs(k.float().mean().item() - 0.5) < 0.01 and set(k.unique().tolist()) == {0, 1}
+    assert not torch.equal(masks[1], masks[2])                     # the paths of one step draw different masks
+    keeps = tuple(k.bool().cpu() for k in masks)
+    (vl, nl, gl), grads, (pv, pn, gpn) = O.train_step_grads(params, fv, fn, gt_verb, gt_nouns, t, c, 2001, keeps, 0.5,
+                                                            pred_verbs=mpv.argmax(-1).cpu())
+    errs = grad_errors(m, grads)
+    report("philox_dropout_step_vs_oracle", logits={"verb": relmax(mpv, pv), "pred_nouns": relmax(mpn, pn),
+                                                    "gt_nouns": relmax(mgpn, gpn)}, grads=errs)
+    assert relmax(mpv, pv) <= BF16_TOL and relmax(mpn, pn) <= BF16_TOL and relmax(mgpn, gpn) <= BF16_TOL
+    for mine, ref in ((lv, vl), (ln, nl), (lg, gl)):
+        assert abs(mine.item() - float(ref)) <= 2e-3 * float(ref)
+    for k, e in errs.items():
+        assert e <= 3e-2, (k, e)
+    m(fv.cuda(), gt_verb.cuda(), img_nouns=fn.cuda())              # the next step draws a new seed
+    assert not torch.equal(m.last_drop_seed, seed)
+    assert not torch.equal(m.dropout_mask(1, B * 6), masks[1])
+    assert torch.equal(m.dropout_mask(1, B * 6, seed), masks[1])   # and a seed reproduces its mask
+
+
+def test_compact_rows_equal_one_row_per_slot(enc_syn):
+    """Pad-row dedup (srg_set_compact_rows): materialising only the real role nodes plus ONE shared pad row gives the
+    same logits, bit for bit, as the reference's layout of R rows per image (every row's arithmetic is unchanged; the
+    pad rows of a batch are copies of one trajectory), and the same gradients up to the order of the sums."""
+    B, D = 41, 2048
+    params = O.init_params(504, 190, 2001, D, seed=0)
+    fv, fn, gt_verb, gt_nouns = [x.cuda() for x in make_batch(enc_syn, B, D, seed=31)]
+    keeps = tuple(k.to(torch.uint8).cuda() for k in _keep_masks(B, D, seed=3))
+    out = []
+    for compact in (True, False):
+        m = model_from(params, enc_syn, D, "bf16").train()
+        m._engine_for(torch.device("cuda", 0)).set_compact_rows(compact)
+        m.dropout_masks = keeps
+        pv, pn, gpn = m(fv, gt_verb, img_nouns=fn)
+        (m.verb_loss(pv, gt_verb) + m.nouns_loss(pn, gt_nouns)).backward()
+        out.append(((pv.detach().clone(), pn.detach().clone(), gpn.detach().clone()),
+                    {k: p.grad.detach().clone() for k, p in m.named_parameters()}))
+    (la, ga), (lb, gb) = out
+    for x, y in zip(la, lb):
+        assert torch.equal(x, y)
+    for k in ga:
+        assert relmax(ga[k], gb[k]) <= 2e-3, (k, relmax(ga[k], gb[k]))
 
 
 def test_full_batch_gradients_vs_oracle(enc_syn):
