@@ -328,8 +328,11 @@ def run_ours(args):
     executed_flops_per_step = sum(fl_k[k] for k in range(kinds)) / args.steps * world   # all ranks
     roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": peaks["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": top["tflops"] / peaks["bf16_sustained"],
+                "achieved_note": "FLOPs the kernel executed (2*M*N*K with the device-resident row count of the compact "
+                                 "role-node layout: real role nodes + one shared pad row) / CUDA-event time of its "
+                                 "launches inside a step; the step_* fields below use the algorithmic 6.547 GFLOP/image",
                 "traffic": NCU_TRAFFIC_BYTES.get(top["kernel"]) if Bl == 6144 else None,
-                "traffic_note": "bytes of one noun-path launch (M=36864) of this kernel, ncu --set full, profiles/",
+                "traffic_note": "bytes of one noun-path launch of this kernel, ncu --set full, profiles/",
                 "peak_source": peaks["source"] + " (sustained bf16; burst %.1f)" % peaks["bf16_burst"],
                 "peak_burst": peaks["bf16_burst"], "frac_burst": top["tflops"] / peaks["bf16_burst"],
                 "step_frac_burst": value * FLOP_PER_IMAGE_FWD_BWD / 1e12 / world / peaks["bf16_burst"],

@@ -46,7 +46,12 @@ int srg_profile_end(int max_kinds, double* ms, double* flops, long long* launche
     const int k = g_prof.kind[i];
     if (k >= 0 && k < max_kinds) {
       ms[k] += t;
-      flops[k] += g_prof.flops[i];
+      // executed FLOPs: with device-resident sizes, the rows / K the kernel actually processed
+      double f = g_prof.flops[i];
+      const int m_rt = g_prof.rt ? g_prof.rt[2 * i] : -1, k_rt = g_prof.rt ? g_prof.rt[2 * i + 1] : -1;
+      if (m_rt >= 0) f = g_prof.mn[i] * m_rt * g_prof.kb_host[i] * kBlockK;
+      if (k_rt >= 0) f = g_prof.mn[i] * g_prof.m_host[i] * static_cast<double>(g_prof.nseg[i]) * k_rt;
+      flops[k] += f;
       launches[k] += 1;
     }
   }

@@ -47,12 +47,25 @@ inline int launch_gemm_inst(const GemmProblem& p, const GemmMaps& maps, const Ge
       SRG_CUDA(cudaEventCreate(&g_prof.ev1[rec]));
       g_prof.created = rec + 1;
     }
+    if (g_prof.rt == nullptr)
+      SRG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_prof.rt), sizeof(int) * 2 * kProfMaxRecords, cudaHostAllocDefault));
     g_prof.kind[rec] = prof_kind(EPI, A_MN, B_MN);
     g_prof.flops[rec] = 2.0 * p.M * static_cast<double>(p.N) * args.total_kb * kBlockK;
+    g_prof.m_host[rec] = p.M;
+    g_prof.nseg[rec] = p.nseg;
+    g_prof.kb_host[rec] = args.total_kb;
+    g_prof.mn[rec] = 2.0 * static_cast<double>(p.N);
+    g_prof.rt[2 * rec] = g_prof.rt[2 * rec + 1] = -1;
     SRG_CUDA(cudaEventRecord(g_prof.ev0[rec], stream));
   }
   SRG_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, args));
-  if (rec >= 0) SRG_CUDA(cudaEventRecord(g_prof.ev1[rec], stream));
+  if (rec >= 0) {
+    SRG_CUDA(cudaEventRecord(g_prof.ev1[rec], stream));
+    if (p.m_dev != nullptr)
+      SRG_CUDA(cudaMemcpyAsync(&g_prof.rt[2 * rec], p.m_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (p.k_dev != nullptr)
+      SRG_CUDA(cudaMemcpyAsync(&g_prof.rt[2 * rec + 1], p.k_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return SRG_OK;
 }

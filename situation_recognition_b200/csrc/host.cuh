@@ -78,7 +78,12 @@ struct ProfState {
   cudaEvent_t ev1[kProfMaxRecords];
   int created = 0;
   int kind[kProfMaxRecords];
-  double flops[kProfMaxRecords];
+  double flops[kProfMaxRecords];       // 2*M*N*K with the host-side (upper bound) sizes
+  // device-resident sizes (GemmArgs::m_dev / k_dev) of the launch, copied to pinned host memory on the launching stream
+  // right after the kernel, so that the executed FLOPs are counted with the row counts the kernel really saw
+  int* rt = nullptr;                   // pinned [kProfMaxRecords][2] = {M, K per segment}, -1 = static
+  double mn[kProfMaxRecords];          // 2 * N * (K / M for the two cases below)
+  int m_host[kProfMaxRecords], nseg[kProfMaxRecords], kb_host[kProfMaxRecords];
 };
 inline ProfState g_prof;
 #ifdef SRG_EPI_TIMING
