@@ -223,7 +223,10 @@ def run_ours(args):
     # included) from one CUDA graph: at 8 x 768 images the host needs most of the step time to queue the launches.
     # --graph / --no-graph override.
     use_graph = (args.graph or world > 1) and not args.no_graph
-    opt = parallel.FlatAdamax(flat, lr=0.002, max_norm=1.0)      # sr.py:80-83,472-473 as one fused kernel
+    # sr.py:80-83,472-473 as one fused kernel; sharded over the ranks when N > 1 (reduce-scatter of the gradient, clip +
+    # Adamax on 1/N of the parameters, all-gather of the parameters) unless --replicated-optimizer
+    sharded = world > 1 and not args.replicated_optimizer
+    opt = parallel.FlatAdamax(flat, lr=0.002, max_norm=1.0, group=dist.group.WORLD if sharded else None)
     params = [p for p in model.parameters() if p.requires_grad]
 
     Bg = args.batch
@@ -245,7 +248,8 @@ def run_ours(args):
         nl = model.nouns_loss(pred_nouns, n)
         gl = model.nouns_loss(gt_pred_nouns, n)                # logged, never back-propagated (sr.py:70,76)
         (vl + nl).backward()
-        flat.all_reduce()
+        if not sharded:
+            flat.all_reduce()
         opt.step()                                              # clip_grad_norm_(1) + Adamax (sr.py:81-82)
         return torch.stack([vl.detach(), nl.detach(), gl.detach()])
 
@@ -392,6 +396,8 @@ def run_ours(args):
                            "max_roles": 6, "T": 4, "parallelism": "dp%d" % world,
                            "step": "zero_grad+fwd(verb,pred-noun,gt-noun)+3 losses+bwd+allreduce+clip+adamax",
                            "launch": "cuda_graph_replay" if use_graph else "eager",
+                           "collectives": ("reduce_scatter(grads)+allreduce(norm)+all_gather(params), sharded clip+adamax"
+                                           if sharded else ("allreduce(grads)" if world > 1 else "none")),
                            "preheat_s": round(preheat_s, 2), "preheat_steps": n_heat,
                            "timed_region_s": round(total_ms / 1e3, 3),
                            "l2": "working set per step (GBs of activations) >> 126 MB L2; no explicit flush",
@@ -422,6 +428,8 @@ def main():
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--preheat", type=float, default=3.0, help="seconds of untimed back-to-back steps before timing")
+    ap.add_argument("--replicated-optimizer", action="store_true",
+                    help="N > 1: all-reduce the gradient and run clip + Adamax on every rank (round-1 scheme)")
     ap.add_argument("--graph", action="store_true", help="replay the whole training step from one CUDA graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -193,6 +193,14 @@ int srg_chain_finalize(srg_handle* h, const srg_grads* g, void* stream);
 int srg_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
                     float beta2, float eps, float max_norm, float* scratch, void* stream);
 
+/* The two halves of srg_clip_adamax for a data-parallel caller that SHARDS the flat buffers over its ranks (each rank
+ * updates 1/N of the parameters after a reduce-scatter of the gradients, then the parameters are all-gathered):
+ * srg_sumsq writes sum x^2 of the local gradient shard to *out (device fp32), the caller all-reduces that scalar, and
+ * srg_adamax_step clips with the global *norm_sq and applies Adamax to the shard (step: device fp32 counter, incremented). */
+int srg_sumsq(const float* x, int64_t n, float* out, void* stream);
+int srg_adamax_step(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float max_norm, const float* norm_sq, float* step, void* stream);
+
 /* Raw tensor-core GEMM (tests / micro-benchmarks):  C[M,N] = alpha * A[M,K] * B[N,K]^T + bias[N]
  * a_mn / b_mn = 1: the operand is stored transposed (A as [K,M], B as [K,N]).  c_dtype: SRG_DT_F32 | SRG_DT_BF16.
  * reduce = 1 (fp32 only): C += ... with k_splits-way split-K. */

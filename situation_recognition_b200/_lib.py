@@ -55,6 +55,8 @@ SIGNATURES = {
     "srg_set_deferred_chain": (_i, [_vp, _i, _vp]),
     "srg_chain_finalize": (_i, [_vp, _c.POINTER(SrgGrads), _vp]),
     "srg_clip_adamax": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp, _vp]),
+    "srg_sumsq": (_i, [_vp, _i64, _vp, _vp]),
+    "srg_adamax_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
     "srg_launch_count": (_c.c_longlong, []),
     "srg_profile_begin": (_i, []),
     "srg_profile_end": (_i, [_i, _vp, _vp, _vp]),

@@ -937,6 +937,18 @@ int srg_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf,
                             static_cast<cudaStream_t>(stream));
 }
 
+int srg_sumsq(const float* x, int64_t n, float* out, void* stream) {
+  SRG_CHECK(x && out, "srg_sumsq: null argument");
+  return launch_sumsq(x, n, out, static_cast<cudaStream_t>(stream));
+}
+
+int srg_adamax_step(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float max_norm, const float* norm_sq, float* step, void* stream) {
+  SRG_CHECK(params && grads && exp_avg && exp_inf && norm_sq && step, "srg_adamax_step: null argument");
+  return launch_adamax_step(params, grads, exp_avg, exp_inf, n, lr, beta1, beta2, eps, max_norm, norm_sq, step,
+                            static_cast<cudaStream_t>(stream));
+}
+
 int srg_set_deferred_chain(srg_handle* h, int on, void* stream) {
   SRG_CHECK(h != nullptr, "srg_set_deferred_chain: null handle");
   DeviceGuard guard_(h->device);

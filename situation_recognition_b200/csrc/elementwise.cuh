@@ -119,6 +119,11 @@ int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows,
 
 
 // clip_grad_norm_(max_norm) + Adamax on flat fp32 buffers (sr.py:80-83).  scratch: device fp32 [2] = {sum g^2, step}.
+// the two halves of launch_clip_adamax, for a caller that shards the flat buffers over ranks and all-reduces the
+// squared norm in between: out = sum x^2 (device scalar, overwritten); then clip with the given *norm_sq + Adamax + ++*step
+int launch_sumsq(const float* x, int64_t n, float* out, cudaStream_t s);
+int launch_adamax_step(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float max_norm, const float* norm_sq, float* step, cudaStream_t s);
 int launch_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
                        float beta2, float eps, float max_norm, float* norm_sq, float* step, cudaStream_t s);
 

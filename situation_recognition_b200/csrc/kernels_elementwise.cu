@@ -1219,19 +1219,33 @@ int launch_pack_bias3(const float* a, const float* b, const float* c, float scal
   return SRG_OK;
 }
 
-int launch_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
-                       float beta2, float eps, float max_norm, float* norm_sq, float* step, cudaStream_t s) {
+int launch_sumsq(const float* x, int64_t n, float* out, cudaStream_t s) {
+  if (n % 4 != 0) return set_error(SRG_ERR_ARG, "sumsq: length %lld must be a multiple of 4", (long long)n);
+  SRG_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
   if (n <= 0) return SRG_OK;
-  if (n % 4 != 0) return set_error(SRG_ERR_ARG, "clip_adamax: flat length %lld must be a multiple of 4", (long long)n);
-  SRG_CUDA(cudaMemsetAsync(norm_sq, 0, sizeof(float), s));
-  k_sumsq<<<grid_for(n / 4, kThreads, 148 * 4), kThreads, 0, s>>>(grads, n / 4, norm_sq);
+  k_sumsq<<<grid_for(n / 4, kThreads, 148 * 4), kThreads, 0, s>>>(x, n / 4, out);
   SRG_LAUNCH_CHECK();
-  k_clip_adamax<<<grid_for(n / 4), kThreads, 0, s>>>(params, grads, exp_avg, exp_inf, n / 4, lr, beta1, beta2, eps,
-                                                     max_norm, norm_sq, step);
-  SRG_LAUNCH_CHECK();
+  return SRG_OK;
+}
+
+int launch_adamax_step(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float max_norm, const float* norm_sq, float* step, cudaStream_t s) {
+  if (n % 4 != 0) return set_error(SRG_ERR_ARG, "adamax: flat length %lld must be a multiple of 4", (long long)n);
+  if (n > 0) {
+    k_clip_adamax<<<grid_for(n / 4), kThreads, 0, s>>>(params, grads, exp_avg, exp_inf, n / 4, lr, beta1, beta2, eps,
+                                                       max_norm, norm_sq, step);
+    SRG_LAUNCH_CHECK();
+  }
   k_inc<<<1, 1, 0, s>>>(step);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
+}
+
+int launch_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float max_norm, float* norm_sq, float* step, cudaStream_t s) {
+  if (n <= 0) return SRG_OK;
+  SRG_TRY(launch_sumsq(grads, n, norm_sq, s));
+  return launch_adamax_step(params, grads, exp_avg, exp_inf, n, lr, beta1, beta2, eps, max_norm, norm_sq, step, s);
 }
 
 }  // namespace srg

@@ -600,9 +600,9 @@ class FCGGNN(nn.Module):
         """model.py:171-180.  `img_nouns` (extension) lets benchmarks feed different synthetic features to the verb
         and noun paths, as the two backbones would produce.
 
-        The verb path (B nodes) is small next to a noun path (6B nodes) and leaves most SMs idle, so it runs on a side
-        stream concurrently with the gt-verb noun path (which does not depend on it); the predicted-verb noun path
-        waits for it.  autograd replays the same streams, so the two backward passes overlap as well."""
+        The verb path and the predicted-verb noun path that depends on it run on side streams, concurrently with the
+        gt-verb noun path (which depends on neither); autograd replays the same streams, so the verb and the noun
+        backward passes overlap as well."""
         batch_size = img.size(0)
         img_n = img if img_nouns is None else img_nouns
         self._step_seed = None
@@ -625,18 +625,27 @@ class FCGGNN(nn.Module):
             return pred_verb, pred_nouns, gt_pred_nouns
         dev = img.device
         cur = torch.cuda.current_stream(dev)
-        # the weights are packed once, before the fork, so both streams see the same operands
+        # the weights are packed once, before the fork, so all streams see the same operands
         self._engine_for(dev).ensure_packed(self, _prec_code(self.precision))
-        side = self._side_streams.get(dev)
-        if side is None:
-            side = self._side_streams[dev] = torch.cuda.Stream(dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
+        sides = self._side_streams.get(dev)
+        if sides is None:
+            sides = self._side_streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        side_v, side_p = sides
+        # Three chains of dependent launches: the verb node path (B rows), then the predicted-verb role graph that needs
+        # its argmax, and -- independent of both -- the gt-verb role graph.  The first two run on side streams while the
+        # third runs on the caller's stream: whenever a launch of one chain is down to its last, partly filled wave of
+        # tiles, the free SMs take tiles of the other chain's launch (on a 768-image shard a launch is only ~1.2 waves).
+        side_v.wait_stream(cur)
+        with torch.cuda.stream(side_v):
             pred_verb = self.predict_verb(img, batch_size)
+        side_p.wait_stream(side_v)
+        with torch.cuda.stream(side_p):
+            pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1, _feat=feat_n)
         gt_pred_nouns = self.predict_nouns(img_n, gt_verb, batch_size, _mask_slot=2, _feat=feat_n)
-        cur.wait_stream(side)
+        cur.wait_stream(side_p)          # side_p waited for side_v: this joins both
+        pred_verb.record_stream(side_p)
         pred_verb.record_stream(cur)
-        pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1, _feat=feat_n)
+        pred_nouns.record_stream(cur)
         return pred_verb, pred_nouns, gt_pred_nouns
 
     @staticmethod

@@ -83,6 +83,67 @@ def _worker(rank, world, port, out, know_global_batch):
     dist.destroy_process_group()
 
 
+def _worker_sharded_opt(rank, world, port, out):
+    """Two training steps with the SHARDED fused optimizer (reduce-scatter, 1/G clip + Adamax, all-gather)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from situation_recognition_b200 import parallel
+    S, O, enc, params, batch = _setup()
+    m = _model(S, enc, params)
+    flat = parallel.attach(m, flat_params=True)
+    opt = parallel.FlatAdamax(flat, lr=0.01, max_norm=1.0, group=dist.group.WORLD)
+    assert opt.world == 2 and opt.exp_avg.numel() * 2 == flat.flat.numel()
+    m.global_batch = B
+    lo, hi = parallel.shard_range(B, rank, world)
+    for _ in range(2):
+        _step(m, flat, batch, lo, hi)
+        opt.step()                                # no flat.all_reduce(): the reduce-scatter is part of the step
+    sd = opt.state_dict()                         # collective: gathers the sharded state
+    torch.cuda.synchronize()
+    if rank == 0:
+        torch.save({"params": {k: v.detach().cpu().clone() for k, v in m.state_dict().items()},
+                    "norm": opt.total_norm().item(), "exp_inf0": sd["state"][0]["exp_inf"].cpu(),
+                    "step": float(sd["state"][0]["step"])}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_optimizer_equals_replicated(tmp_path):
+    out = str(tmp_path / "opt.pt")
+    mp.spawn(_worker_sharded_opt, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    from situation_recognition_b200 import parallel
+    S, O, enc, params, batch = _setup()
+    m = _model(S, enc, params)
+    flat = parallel.attach(m, flat_params=True)
+    opt = parallel.FlatAdamax(flat, lr=0.01, max_norm=1.0)
+    for _ in range(2):
+        _step(m, flat, batch, 0, B)
+        opt.step()
+    torch.cuda.synchronize()
+    assert got["step"] == 2.0
+    assert abs(got["norm"] - opt.total_norm().item()) <= 5e-3 * opt.total_norm().item()
+    moved = 0.0
+    for k, v in m.state_dict().items():
+        diff = (got["params"][k] - v.cpu()).abs()
+        # the first Adamax step moves every weight by lr * sign(g): elements whose gradient is within the rounding noise of
+        # zero may go either way (see test_graphed_step_matches_eager; W_p / W_x see ~2e-3 of max|g| of bf16 noise from
+        # the per-rank rounding of d/dP); everything else agrees far below the update size
+        assert (diff > 1e-3).float().mean().item() <= 1e-2 and diff.max().item() <= 4 * 0.01 + 1e-3, (k, diff.max().item())
+        moved = max(moved, (v.cpu() - params[k]).abs().max().item())
+    assert moved > 0.01
+    sd = opt.state_dict()
+    assert torch.allclose(got["exp_inf0"], sd["state"][0]["exp_inf"].cpu(), rtol=2e-2, atol=1e-7)
+    # the saved state loads into torch.optim.Adamax (checkpoint compatibility, sr.py:28-41)
+    ref = torch.optim.Adamax([p for p in m.parameters() if p.requires_grad], lr=0.01)
+    ref.load_state_dict(sd)
+    for p in m.parameters():
+        p.grad = torch.zeros_like(p)
+    ref.step()
+
+
 @pytest.mark.parametrize("know_global_batch", [False, True])
 def test_two_cuda_ranks_equal_full_batch(tmp_path, know_global_batch):
     out = str(tmp_path / "ranks.pt")
