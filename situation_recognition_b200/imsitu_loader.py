@@ -16,14 +16,17 @@ class imsitu_loader(data.Dataset):
         self.imgs_names = list(train_json.keys())
         self.encoder = encoder
         self.transform = transform
+        self.skip_images = False     # extension: annotations only (the caller holds cached backbone features)
 
     def __getitem__(self, index):
-        from PIL import Image
         img_name = self.imgs_names[index]
         annotations = self.train_json[img_name]
+        verb, labels = self.encoder.encode(annotations)
+        if self.skip_images:
+            return img_name, torch.empty(0), verb, labels
+        from PIL import Image
         img = Image.open(os.path.join(self.img_dir, img_name)).convert('RGB')
         img = self.transform(img)
-        verb, labels = self.encoder.encode(annotations)
         return img_name, img, verb, labels
 
     def __len__(self):
@@ -33,7 +36,9 @@ class imsitu_loader(data.Dataset):
 class ShardedBatchSampler(data.Sampler):
     """Yields, for every GLOBAL batch of `global_batch` samples, this rank's contiguous slice of it -- the same split
     `nn.DataParallel` makes along dim 0 (sr.py:467-470), but with one process per GPU.  Every rank yields the same
-    number of batches, so the per-step collectives stay aligned; no sample is duplicated or dropped."""
+    number of batches, so the per-step collectives stay aligned.  No sample is dropped; samples are only repeated when
+    the last global batch holds fewer samples than there are ranks (every rank needs at least one).  The shards of the
+    last batch may be unequal: `global_sizes()` tells the loss how many images the whole batch holds."""
 
     def __init__(self, n, global_batch, rank=0, world=1, shuffle=False, seed=0):
         if global_batch < world:
@@ -46,6 +51,10 @@ class ShardedBatchSampler(data.Sampler):
 
     def __len__(self):
         return (self.n + self.gb - 1) // self.gb
+
+    def global_sizes(self):
+        """Images of each GLOBAL batch, in iteration order (the denominator of the verb loss, model.py:184-185)."""
+        return [max(min(self.gb, self.n - i0), self.world) for i0 in range(0, self.n, self.gb)]
 
     def __iter__(self):
         if self.shuffle:

@@ -586,8 +586,8 @@ class FCGGNN(nn.Module):
         out._srg_stats = self._last_stats      # lets nouns_loss() reuse the classifier's per-tile softmax statistics
         return out
 
-    def predict_verb(self, img, batch_size):
-        feat = _as_feat(self.convnet_verbs(img), self.D)
+    def predict_verb(self, img, batch_size, _feat=None):
+        feat = _feat if _feat is not None else _as_feat(self.convnet_verbs(img), self.D)
         if feat.shape[0] != batch_size:
             raise _lib.SrgError("batch_size %d does not match the features (%d)" % (batch_size, feat.shape[0]))
         keep, seed = self._dropout(0, feat.device)
@@ -613,17 +613,35 @@ class FCGGNN(nn.Module):
         finally:
             self._step_seed = None
 
-    def _forward_paths(self, img, img_n, gt_verb, batch_size):
+    def extract_features(self, img, img_nouns=None):
+        """The two frozen backbones (model.py:116,159): (feat_verbs, feat_nouns), fp32 [B, D].  Both are frozen
+        (model.py:17-18), so for a fixed image under a deterministic transform in eval mode these features never
+        change: `features.FeatureCache` keeps them across epochs."""
+        img_n = img if img_nouns is None else img_nouns
+        return _as_feat(self.convnet_verbs(img), self.D), _as_feat(self.convnet_nouns(img_n), self.D)
+
+    def forward_features(self, feat_verbs, feat_nouns, gt_verb):
+        """`forward` on backbone features instead of images: (pred_verb, pred_nouns, gt_pred_nouns)."""
+        fv, fn = _as_feat(feat_verbs, self.D), _as_feat(feat_nouns, self.D)
+        self._step_seed = None
+        if self.training and self.dropout_masks is None:
+            self._step_seed = self._draw_seed(fv.device)
+        try:
+            return self._forward_paths(None, None, gt_verb, fv.shape[0], feat_v=fv, feat_n=fn)
+        finally:
+            self._step_seed = None
+
+    def _forward_paths(self, img, img_n, gt_verb, batch_size, feat_v=None, feat_n=None):
         # the noun backbone is frozen and deterministic in eval mode: evaluate it once for both noun passes
-        feat_n = None
-        if img_n.is_cuda and not (self.training and _has_batchnorm_in_train(self.convnet_nouns)):
+        if feat_n is None and img_n.is_cuda and not (self.training and _has_batchnorm_in_train(self.convnet_nouns)):
             feat_n = _as_feat(self.convnet_nouns(img_n), self.D)
-        if not (self.overlap_streams and img.is_cuda):
-            pred_verb = self.predict_verb(img, batch_size)
+        on_cuda = (feat_v if feat_v is not None else img).is_cuda
+        if not (self.overlap_streams and on_cuda):
+            pred_verb = self.predict_verb(img, batch_size, _feat=feat_v)
             pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1, _feat=feat_n)
             gt_pred_nouns = self.predict_nouns(img_n, gt_verb, batch_size, _mask_slot=2, _feat=feat_n)
             return pred_verb, pred_nouns, gt_pred_nouns
-        dev = img.device
+        dev = (feat_v if feat_v is not None else img).device
         cur = torch.cuda.current_stream(dev)
         # the weights are packed once, before the fork, so all streams see the same operands
         self._engine_for(dev).ensure_packed(self, _prec_code(self.precision))
@@ -637,7 +655,7 @@ class FCGGNN(nn.Module):
         # tiles, the free SMs take tiles of the other chain's launch (on a 768-image shard a launch is only ~1.2 waves).
         side_v.wait_stream(cur)
         with torch.cuda.stream(side_v):
-            pred_verb = self.predict_verb(img, batch_size)
+            pred_verb = self.predict_verb(img, batch_size, _feat=feat_v)
         side_p.wait_stream(side_v)
         with torch.cuda.stream(side_p):
             pred_nouns = self.predict_nouns(img_n, torch.argmax(pred_verb, 1), batch_size, _mask_slot=1, _feat=feat_n)

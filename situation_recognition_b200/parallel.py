@@ -77,6 +77,19 @@ def attach(model, group=None, flat_params=False):
     return flat
 
 
+def broadcast_model(model, src=0, group=None):
+    """Every rank constructs the model itself (random init of the GGNN stage, possibly of the backbones): make rank
+    `src`'s parameters and buffers everyone's.  The reference has ONE process whose `nn.DataParallel` re-broadcasts the
+    parameters at every step (sr.py:467-470); here they are sent once, and stay identical because every rank applies
+    the same update to the same all-reduced gradient."""
+    if _world(group) <= 1:
+        return
+    with torch.no_grad():
+        for t in model.state_dict().values():
+            if torch.is_tensor(t):
+                dist.broadcast(t, src=src, group=group)
+
+
 class FlatParams(FlatGrads):
     """Parameters AND gradients of the trainable tensors as two flat fp32 buffers (each tensor keeps its shape as a
     view), so clip + optimizer run as one fused kernel over contiguous memory (`FlatAdamax`)."""

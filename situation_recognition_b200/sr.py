@@ -8,7 +8,13 @@ ways.  Differences, all forced by the B200-first design:
     `nn.DataParallel`; `--batch_size` stays the GLOBAL batch and is split contiguously over the ranks;
   * no `GradScaler`/autocast: the stage computes in bf16 with fp32 accumulation and needs no loss scaling;
   * the scorer is the vectorised one (identical numbers); rank 0 prints and writes checkpoints;
-  * `--no_pretrained` (extra flag) skips the ImageNet weights when there is no network.
+  * clip_grad_norm_ + Adamax (sr.py:80-83) run as the fused `parallel.FlatAdamax` step over flat parameter / gradient
+    buffers, sharded over the ranks (reduce-scatter, 1/N update, all-gather); its `state_dict()` has torch.optim.Adamax's
+    format, so checkpoints load into the reference's optimizer and vice versa;
+  * the features of the frozen backbones on the dev / test images are cached across epochs (`features.FeatureCache`):
+    the per-epoch validation (sr.py:123) runs the backbones once, not once per epoch;
+  * `--no_pretrained` (extra flag) skips the ImageNet weights when there is no network; `--no_feature_cache` disables
+    the cache.
 """
 import os
 from argparse import ArgumentParser
@@ -21,6 +27,7 @@ import torch
 import torch.distributed as dist
 
 from . import parallel
+from .features import FeatureCache
 from .imsitu_encoder import imsitu_encoder
 from .imsitu_loader import ShardedBatchSampler, imsitu_loader
 from .imsitu_scorer import imsitu_scorer
@@ -68,8 +75,13 @@ def _print_scores(prefix, losses, top1_a, top5_a, avg_score, tail):
                                                    format_dict(gt, '{:.2f}', ''), avg_score, tail))
 
 
+def _global_sizes(loader):
+    sampler = getattr(loader, "batch_sampler", None)
+    return sampler.global_sizes() if hasattr(sampler, "global_sizes") else None
+
+
 def train(model, train_loader, dev_loader, optimizer, max_epoch, encoder, model_saving_name, folder, checkpoint=None,
-          flat=None, plot=True):
+          flat=None, plot=True, dev_cache=None):
     """sr.py:15-162."""
     model.train()
     hist = {k: [] for k in ('avg_scores', 'verb_losses', 'nouns_losses', 'val_avg_scores', 'val_verb_losses',
@@ -85,6 +97,8 @@ def train(model, train_loader, dev_loader, optimizer, max_epoch, encoder, model_
         flat = parallel.attach(model)
     params = [p for p in model.parameters() if p.requires_grad]
     dev = next(model.parameters()).device
+    fused = getattr(optimizer, "fused_clip", False)          # parallel.FlatAdamax: clip (+ gradient exchange) inside step()
+    sharded = getattr(optimizer, "world", 1) > 1
 
     for e in range(epoch, max_epoch):
         sums = torch.zeros(3, device=dev)
@@ -92,16 +106,20 @@ def train(model, train_loader, dev_loader, optimizer, max_epoch, encoder, model_
         top1, top5 = imsitu_scorer(encoder, 1, 3), imsitu_scorer(encoder, 5, 3)
         if hasattr(train_loader.batch_sampler, 'set_epoch'):
             train_loader.batch_sampler.set_epoch(e)
-        for _, img, verb, nouns in train_loader:
+        sizes = _global_sizes(train_loader)
+        for step, (_, img, verb, nouns) in enumerate(train_loader):
             img, verb, nouns = img.to(dev, non_blocking=True), verb.to(dev), nouns.to(dev)
+            model.global_batch = sizes[step] if sizes is not None else None
             flat.zero()
             pred_verb, pred_nouns, pred_gt_nouns = model(img, verb)
             verb_loss = model.verb_loss(pred_verb, verb)
             nouns_loss = model.nouns_loss(pred_nouns, nouns)
             gt_nouns_loss = model.nouns_loss(pred_gt_nouns, nouns)
             (verb_loss + nouns_loss).backward()
-            flat.all_reduce()
-            torch.nn.utils.clip_grad_norm_(params, 1)
+            if not sharded:
+                flat.all_reduce()
+            if not fused:
+                torch.nn.utils.clip_grad_norm_(params, 1)
             optimizer.step()
             top1.add_point_both(pred_verb, verb, pred_nouns, nouns, pred_gt_nouns)
             top5.add_point_both(pred_verb, verb, pred_nouns, nouns, pred_gt_nouns)
@@ -115,17 +133,18 @@ def train(model, train_loader, dev_loader, optimizer, max_epoch, encoder, model_
         hist['nouns_losses'].append(means[1])
         _print_scores('training losses = [v: {:.2f}, n: {:.2f}, gt: {:.2f}]', means, top1_a, top5_a, avg_score, '-' * 50)
 
-        top1, top5, val_losses, val_avg_score = eval(model, dev_loader, encoder, logging=True)
+        top1, top5, val_losses, val_avg_score = eval(model, dev_loader, encoder, logging=True, cache=dev_cache)
         model.train()
         hist['val_avg_scores'].append(val_avg_score)
         hist['val_verb_losses'].append(val_losses['verb_loss'])
         hist['val_nouns_losses'].append(val_losses['nouns_loss'])
 
+        opt_state = optimizer.state_dict()          # a collective when the optimizer state is sharded: every rank calls it
         if _rank_world()[0] == 0:
             if plot:
                 _plot(hist, pjoin(folder, model_saving_name + '.png'))
             ckpt = {'epoch': e + 1, **hist, 'model_state_dict': model.state_dict(),
-                    'optimizer_state_dict': optimizer.state_dict()}
+                    'optimizer_state_dict': opt_state}
             torch.save(ckpt, pjoin(folder, model_saving_name))
 
 
@@ -148,20 +167,32 @@ def _plot(hist, path):
     plt.clf()
 
 
-def eval(model, loader, encoder, logging=False):
-    """sr.py:165-232."""
+def eval(model, loader, encoder, logging=False, cache=None):
+    """sr.py:165-232.  cache (FeatureCache, optional): the frozen backbones' features of this loader's images are kept
+    across calls; once every image is cached the loader stops decoding images altogether."""
     model.eval()
     dev = next(model.parameters()).device
     sums = torch.zeros(3, device=dev)
     top1, top5 = imsitu_scorer(encoder, 1, 3), imsitu_scorer(encoder, 5, 3)
+    dataset = getattr(loader, "dataset", None)
+    if cache is not None and dataset is not None and hasattr(dataset, "skip_images"):
+        dataset.skip_images = cache.has(dataset.imgs_names)       # read by the workers this iteration starts
+    sizes = _global_sizes(loader)
     with torch.no_grad():
-        for _, img, verb, nouns in loader:
-            img, verb, nouns = img.to(dev, non_blocking=True), verb.to(dev), nouns.to(dev)
-            pred_verb, pred_nouns, pred_gt_nouns = model(img, verb)
+        for step, (names, img, verb, nouns) in enumerate(loader):
+            verb, nouns = verb.to(dev), nouns.to(dev)
+            model.global_batch = sizes[step] if sizes is not None else None
+            if cache is not None:
+                fv, fn = cache.features(model, list(names), img.to(dev, non_blocking=True) if img.numel() else None)
+                pred_verb, pred_nouns, pred_gt_nouns = model.forward_features(fv, fn, verb)
+            else:
+                pred_verb, pred_nouns, pred_gt_nouns = model(img.to(dev, non_blocking=True), verb)
             top1.add_point_both(pred_verb, verb, pred_nouns, nouns, pred_gt_nouns)
             top5.add_point_both(pred_verb, verb, pred_nouns, nouns, pred_gt_nouns)
             sums += torch.stack([model.verb_loss(pred_verb, verb), model.nouns_loss(pred_nouns, nouns),
                                  model.nouns_loss(pred_gt_nouns, nouns)])
+    if dataset is not None and hasattr(dataset, "skip_images"):
+        dataset.skip_images = False
     v, n, g = (_all_sum(sums) / len(loader)).tolist()
     val_losses = {'verb_loss': v, 'nouns_loss': n, 'gt_loss': g}
     avg_score = 0
@@ -290,6 +321,10 @@ def build_parser():
     # extensions (not in the reference)
     parser.add_argument("--no_pretrained", action="store_true", help="random-init backbones (no network access)")
     parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
+    parser.add_argument("--no_feature_cache", action="store_true",
+                        help="recompute the frozen backbones on the dev set at every epoch, like the reference")
+    parser.add_argument("--torch_optimizer", action="store_true",
+                        help="torch.optim.Adamax + clip_grad_norm_ + gradient all-reduce instead of the fused sharded step")
     return parser
 
 
@@ -304,8 +339,10 @@ def main(argv=None):
     if not torch.cuda.is_available():
         raise SystemExit("situation_recognition_b200.sr needs a B200 GPU: the GGNN stage has no CPU path")
     if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group("nccl")
+        # one process per GPU; SRG_DIST_BACKEND=gloo lets several ranks share one GPU (tests on a single-GPU box: NCCL
+        # refuses two ranks on the same device)
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count())
+        dist.init_process_group(os.environ.get("SRG_DIST_BACKEND", "nccl"))
     rank, world = _rank_world()
     dev = torch.device("cuda", torch.cuda.current_device())
     Path(args.saving_folder).mkdir(exist_ok=True)
@@ -333,11 +370,22 @@ def main(argv=None):
     dev_loader = _loader(dev_set, args.batch_size, False, args.num_workers)
     test_loader = _loader(test_set, args.batch_size, True, args.num_workers)
 
+    seed = os.environ.get("SRG_SEED")            # extension: repeatable initial weights / dropout (tests)
+    if seed is not None:
+        torch.manual_seed(int(seed))
     model = FCGGNN(encoder, D_hidden_state=2048, precision=args.precision,
                    pretrained=False if args.no_pretrained else None).to(dev)
+    parallel.broadcast_model(model)              # every rank built its own random init: rank 0's becomes everyone's
+    if seed is not None:
+        torch.manual_seed(int(seed) + 1000 * rank)      # per-rank dropout streams from here on
     _print0('Using', world, 'GPUs!')
-    flat = parallel.attach(model)
-    optimizer = torch.optim.Adamax(filter(lambda p: p.requires_grad, model.parameters()), lr=args.lr)
+    if args.torch_optimizer:
+        flat = parallel.attach(model)
+        optimizer = torch.optim.Adamax(filter(lambda p: p.requires_grad, model.parameters()), lr=args.lr)
+    else:   # sr.py:80-83,472-473 as one fused kernel over flat buffers, sharded over the ranks
+        flat = parallel.attach(model, flat_params=True)
+        optimizer = parallel.FlatAdamax(flat, lr=args.lr, max_norm=1.0, group=dist.group.WORLD if world > 1 else None)
+    dev_cache = None if args.no_feature_cache else FeatureCache(len(dev_set), 2048, dev)
     torch.backends.cudnn.benchmark = True
 
     if len(args.resume_model) > 1:
@@ -367,7 +415,7 @@ def main(argv=None):
     else:
         _print0('Model training started!')
         train(model, train_loader, dev_loader, optimizer, args.epochs, encoder, args.model_saving_name,
-              folder=args.saving_folder, checkpoint=checkpoint, flat=flat)
+              folder=args.saving_folder, checkpoint=checkpoint, flat=flat, dev_cache=dev_cache)
     if world > 1:
         dist.destroy_process_group()
 

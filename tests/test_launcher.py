@@ -61,16 +61,25 @@ def test_all_modes_end_to_end(tmp_path, capsys, monkeypatch):
     first = _make_dataset(str(tmp_path))
     monkeypatch.chdir(tmp_path)
     common = ["--no_pretrained", "--num_workers", "0", "--batch_size", "4"]
-    sr.main(common + ["--train_file", "tiny.json", "--epochs", "1", "--model_saving_name", "tiny"])
+    sr.main(common + ["--train_file", "tiny.json", "--epochs", "2", "--model_saving_name", "tiny"])
     out = capsys.readouterr().out
-    assert "Model training started!" in out and "Epoch-0, lr: 0.0020" in out
+    assert "Model training started!" in out and "Epoch-0, lr: 0.0020" in out and "Epoch-1, lr: 0.0020" in out
+    # the frozen backbones' dev-set features are cached: the second epoch's validation reports the same kind of line and
+    # (same weights for the backbones, updated GGNN) runs without touching the images again
+    assert len(re.findall(r"val losses = \[v:", out)) == 2
     assert re.search(r"training losses = \[v: \d+\.\d\d, n: \d+\.\d\d, gt: \d+\.\d\d\]", out)
     assert re.search(r"1-verb: \d+\.\d\d, 1-value: \d+\.\d\d, 1-value-all: \d+\.\d\d", out)
     ckpt = torch.load(tmp_path / "checkpoints" / "tiny", weights_only=False)
     assert set(ckpt) == {'epoch', 'avg_scores', 'verb_losses', 'nouns_losses', 'val_avg_scores', 'val_verb_losses',
                          'val_nouns_losses', 'model_state_dict', 'optimizer_state_dict'}            # sr.py:145-157
-    assert ckpt['epoch'] == 1 and 'ggsnn.W_p.weight' in ckpt['model_state_dict']
+    assert ckpt['epoch'] == 2 and 'ggsnn.W_p.weight' in ckpt['model_state_dict']
     assert 'convnet_verbs.model.conv1.weight' in ckpt['model_state_dict']
+    # the fused optimizer's state has torch.optim.Adamax's format: 20 trainable tensors, and torch's Adamax loads it
+    osd = ckpt['optimizer_state_dict']
+    assert len(osd['state']) == 20 and set(osd['state'][0]) == {'step', 'exp_avg', 'exp_inf'}
+    assert float(osd['state'][0]['step']) == 4.0                      # 6 images / batch 4 = 2 steps per epoch
+    ps = [torch.nn.Parameter(torch.zeros_like(osd['state'][i]['exp_avg'])) for i in range(20)]
+    torch.optim.Adamax(ps, lr=0.002).load_state_dict(osd)
     sr.main(common + ["--resume_model", "tiny", "--evaluate_dev"])
     out = capsys.readouterr().out
     assert "Loading encoder file" in out and "=> evaluating model with dev-set..." in out and "val losses = [v:" in out
@@ -82,3 +91,47 @@ def test_all_modes_end_to_end(tmp_path, capsys, monkeypatch):
     sr.main(common + ["--resume_model", "tiny", "--subset", "2"])
     out = capsys.readouterr().out
     assert out.count("Analizing: ") == 2 and "---- Ground truth ----" in out
+
+
+@pytest.mark.gpu
+def test_two_rank_launcher(tmp_path):
+    """`torchrun --nproc-per-node 2 -m situation_recognition_b200.sr`: sharded loader (unequal shards: 6 images over
+    global batches of 4 -> 2+2, then 1+1), global loss denominators, sharded fused optimizer, rank-0 checkpoint.  On a
+    single-GPU box the two ranks share the GPU and exchange through gloo (SRG_DIST_BACKEND); with two or more GPUs the
+    same command runs on NCCL.  The resulting weights must equal a single-process run of the same two epochs."""
+    import subprocess
+    import sys
+    from situation_recognition_b200 import sr
+    _make_dataset(str(tmp_path))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    args = ["--no_pretrained", "--num_workers", "0", "--batch_size", "4", "--train_file", "tiny.json", "--epochs", "2",
+            "--no_feature_cache"]
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), SRG_SEED="7")
+    if torch.cuda.device_count() < 2:
+        env["SRG_DIST_BACKEND"] = "gloo"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", "-m", "situation_recognition_b200.sr"] + args + \
+          ["--model_saving_name", "two"]
+    res = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "Using 2 GPUs!" in res.stdout and res.stdout.count("training losses = [v:") == 2      # rank 0 prints once
+    res1 = subprocess.run([sys.executable, "-m", "situation_recognition_b200.sr"] + args + ["--model_saving_name", "one"],
+                          cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=900)
+    assert res1.returncode == 0, res1.stdout[-3000:] + res1.stderr[-3000:]
+    two = torch.load(tmp_path / "checkpoints" / "two", weights_only=False)
+    one = torch.load(tmp_path / "checkpoints" / "one", weights_only=False)
+    assert two["epoch"] == one["epoch"] == 2
+    # same data order and initial weights (SRG_SEED + the rank-0 broadcast).  The runs agree statistically, not bit for
+    # bit: the dropout masks differ (Philox is keyed by the local row) and the backbones' BatchNorm layers are in training
+    # mode (sr.py:24), so a rank normalises with the statistics of its 2-image shard -- exactly as a DataParallel replica
+    # does.  Exact equality of sharded and full-batch gradients is tests/test_parallel_cuda.py's job.
+    import math
+    for k in ("verb_losses", "nouns_losses", "val_verb_losses", "val_nouns_losses"):
+        assert len(two[k]) == len(one[k]) == 2
+        for a, b in zip(two[k], one[k]):
+            assert math.isfinite(a) and math.isfinite(b) and 0.5 * b <= a <= 2.0 * b, (k, two[k], one[k])
+    init = {k: v for k, v in one["model_state_dict"].items() if k.startswith("ggsnn.")}
+    w2, w1 = two["model_state_dict"]["ggsnn.U_z.weight"], one["model_state_dict"]["ggsnn.U_z.weight"]
+    assert (w2 - w1).abs().max().item() <= 2 * 4 * 0.002 + 1e-4            # 4 steps of at most lr each, both ways
+    assert torch.equal(two["model_state_dict"]["convnet_nouns.model.conv1.weight"],
+                       one["model_state_dict"]["convnet_nouns.model.conv1.weight"])      # frozen, broadcast from rank 0
