@@ -43,8 +43,10 @@ def available(path=REF_COPY):
                                                                                            "imsitu_encoder.py"))
 
 
-def load(path=REF_COPY):
-    """(reference `model` module, reference `utils.imsitu_encoder` module) imported from `path`."""
+def load(path=REF_COPY, stub_backbones=True):
+    """(reference `model` module, reference `utils.imsitu_encoder` module) imported from `path`.
+    stub_backbones=False keeps the reference's own `resnet` class (end-to-end runs: the caller makes
+    torchvision.models.resnet152 constructible offline)."""
     import torch
     if not available(path):
         raise FileNotFoundError("no reference copy under %s (run __graft_entry__.build() where /root/reference exists)"
@@ -59,7 +61,8 @@ def load(path=REF_COPY):
             ref_enc = importlib.import_module("utils.imsitu_encoder")
     finally:
         sys.path.remove(path)
-    ref_model.resnet = lambda out_layers: torch.nn.Identity()      # the only patch: backbones -> features pass through
+    if stub_backbones:
+        ref_model.resnet = lambda out_layers: torch.nn.Identity()  # the only patch: backbones -> features pass through
     return ref_model, ref_enc
 
 

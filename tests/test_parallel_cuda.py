@@ -135,7 +135,8 @@ def test_sharded_optimizer_equals_replicated(tmp_path):
         moved = max(moved, (v.cpu() - params[k]).abs().max().item())
     assert moved > 0.01
     sd = opt.state_dict()
-    assert torch.allclose(got["exp_inf0"], sd["state"][0]["exp_inf"].cpu(), rtol=2e-2, atol=1e-7)
+    want = sd["state"][0]["exp_inf"].cpu()
+    assert (got["exp_inf0"] - want).abs().max().item() <= 1e-2 * want.abs().max().item()
     # the saved state loads into torch.optim.Adamax (checkpoint compatibility, sr.py:28-41)
     ref = torch.optim.Adamax([p for p in m.parameters() if p.requires_grad], lr=0.01)
     ref.load_state_dict(sd)
