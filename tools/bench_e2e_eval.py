@@ -94,8 +94,22 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    cpu_line = {}
+    if rank == 0 and not args.no_cpu_reference:
+        # the CPU leg runs FIRST, in a child process that sees no GPU, while the other ranks wait in the rendezvous
+        # (later they would spin in NCCL and compete for the host cores)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS"):
+            env.pop(k, None)
+        try:
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-reference-only", "--cpu-sample",
+                                  str(args.cpu_sample), "--cpu-steps", str(args.cpu_steps)], env=env, capture_output=True,
+                                 text=True, timeout=480)
+            cpu_line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+        except Exception as ex:
+            cpu_line = {"cpu_reference": None, "why": str(ex)[:200]}
     if world > 1:
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     dev = torch.device("cuda", torch.cuda.current_device())
 
     enc = S.imsitu_encoder(make_train_json(seed=0), verbose=False)
@@ -182,18 +196,7 @@ def main():
             "first_epoch_images_per_sec": per_epoch[0]["images_per_sec"],
             "cached_epoch_images_per_sec": per_epoch[-1]["images_per_sec"] if len(per_epoch) > 1 else None,
             "feature_cache_mb_per_gpu": 2 * n_local * 2048 * 4 / 2 ** 20}
-    if rank == 0 and not args.no_cpu_reference:
-        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
-        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS"):
-            env.pop(k, None)
-        try:
-            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-reference-only", "--cpu-sample",
-                                  str(args.cpu_sample), "--cpu-steps", str(args.cpu_steps)], env=env, capture_output=True,
-                                 text=True, timeout=1200)
-            line.update(json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1]))
-        except Exception as ex:
-            line["cpu_reference"] = None
-            line["why"] = str(ex)[:200]
+    line.update(cpu_line)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
