@@ -217,8 +217,6 @@ def run_ours(args):
     model.train()
     if args.cta_group:
         model._engine_for(dev).set_cta_group(args.cta_group)
-    if args.no_tail_split:
-        model._engine_for(dev).set_tail_split(False)
     if args.no_compact_rows:
         model._engine_for(dev).set_compact_rows(False)
     flat = parallel.attach(model, flat_params=True)
@@ -431,7 +429,6 @@ def main():
     ap.add_argument("--batch", type=int, default=6144, help="global batch (BASELINE.json: 6144)")
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-tail-split", action="store_true", help="A/B: do not split the last wave's tiles along K")
     ap.add_argument("--no-compact-rows", action="store_true", help="A/B: R rows per image instead of the compact layout")
     ap.add_argument("--preheat", type=float, default=3.0, help="seconds of untimed back-to-back steps before timing")
     ap.add_argument("--replicated-optimizer", action="store_true",
