@@ -97,14 +97,17 @@ def _worker_sharded_opt(rank, world, port, out):
     assert opt.world == 2 and opt.exp_avg.numel() * 2 == flat.flat.numel()
     m.global_batch = B
     lo, hi = parallel.shard_range(B, rank, world)
-    for _ in range(2):
+    first = None
+    for it in range(2):
         _step(m, flat, batch, lo, hi)
         opt.step()                                # no flat.all_reduce(): the reduce-scatter is part of the step
-    sd = opt.state_dict()                         # collective: gathers the sharded state
+        if it == 0:
+            first = opt.state_dict()["state"][0]["exp_inf"].cpu()     # collective: gathers the sharded state
+    sd = opt.state_dict()
     torch.cuda.synchronize()
     if rank == 0:
         torch.save({"params": {k: v.detach().cpu().clone() for k, v in m.state_dict().items()},
-                    "norm": opt.total_norm().item(), "exp_inf0": sd["state"][0]["exp_inf"].cpu(),
+                    "norm": opt.total_norm().item(), "exp_inf0": first,
                     "step": float(sd["state"][0]["step"])}, out)
     dist.barrier()
     dist.destroy_process_group()
@@ -119,11 +122,17 @@ def test_sharded_optimizer_equals_replicated(tmp_path):
     m = _model(S, enc, params)
     flat = parallel.attach(m, flat_params=True)
     opt = parallel.FlatAdamax(flat, lr=0.01, max_norm=1.0)
-    for _ in range(2):
+    first = None
+    for it in range(2):
         _step(m, flat, batch, 0, B)
         opt.step()
+        if it == 0:
+            first = opt.state_dict()["state"][0]["exp_inf"].cpu()
     torch.cuda.synchronize()
     assert got["step"] == 2.0
+    # after ONE step the optimizer state only differs by the order of the gradient sums (the second step already sees
+    # slightly different weights: see the sign-flip note below)
+    assert (got["exp_inf0"] - first).abs().max().item() <= 1e-3 * first.abs().max().item()
     assert abs(got["norm"] - opt.total_norm().item()) <= 5e-3 * opt.total_norm().item()
     moved = 0.0
     for k, v in m.state_dict().items():
@@ -135,8 +144,6 @@ def test_sharded_optimizer_equals_replicated(tmp_path):
         moved = max(moved, (v.cpu() - params[k]).abs().max().item())
     assert moved > 0.01
     sd = opt.state_dict()
-    want = sd["state"][0]["exp_inf"].cpu()
-    assert (got["exp_inf0"] - want).abs().max().item() <= 1e-2 * want.abs().max().item()
     # the saved state loads into torch.optim.Adamax (checkpoint compatibility, sr.py:28-41)
     ref = torch.optim.Adamax([p for p in m.parameters() if p.requires_grad], lr=0.01)
     ref.load_state_dict(sd)
