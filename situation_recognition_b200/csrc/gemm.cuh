@@ -306,30 +306,33 @@ gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
         const int nb0 = nt * BLOCK_N + static_cast<int>(cta_rank) * B_ROWS;
         const int kb_begin = ks * kb_per_split;
         const int kb_end = min(total_kb, kb_begin + kb_per_split);
-        // locate the first segment
+        // locate the first segment (device-resident K: equally long segments of seg_kb_rt k-blocks)
         int seg = 0, seg_first = 0;
-        if (seg_kb_rt == 0) {
+        if (seg_kb_rt != 0) {
+          seg = kb_begin / seg_kb_rt;
+          seg_first = seg * seg_kb_rt;
+        } else {
           while (seg < args.nseg - 1 && kb_begin >= seg_first + args.seg_kb[seg]) {
             seg_first += args.seg_kb[seg];
             ++seg;
           }
         }
+        int seg_len = (seg_kb_rt != 0) ? seg_kb_rt : args.seg_kb[seg];
+        int seg_col = args.seg_acol[seg];
+        const CUtensorMap* amap = &maps.a[args.seg_map[seg]];
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          if (seg_kb_rt != 0) {               // equally long segments of device-resident length
-            seg = kb / seg_kb_rt;
-            seg_first = seg * seg_kb_rt;
-          } else {
-            while (seg < args.nseg - 1 && kb >= seg_first + args.seg_kb[seg]) {
-              seg_first += args.seg_kb[seg];
-              ++seg;
-            }
+          while (seg < args.nseg - 1 && kb >= seg_first + seg_len) {   // next segment: once per segment, not per k-block
+            seg_first += seg_len;
+            ++seg;
+            seg_len = (seg_kb_rt != 0) ? seg_kb_rt : args.seg_kb[seg];
+            seg_col = args.seg_acol[seg];
+            amap = &maps.a[args.seg_map[seg]];
           }
-          const int ka = args.seg_acol[seg] + (kb - seg_first) * kBlockK;
+          const int ka = seg_col + (kb - seg_first) * kBlockK;
           const int kbcoord = (args.flags & FLAG_BK_A) ? ka : kb * kBlockK;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem_a + stage * A_BYTES;
           uint8_t* sb = smem_b + stage * B_BYTES;
-          const CUtensorMap* amap = &maps.a[args.seg_map[seg]];
           if constexpr (CG == 2) {
             if constexpr (!A_MN) {
               ptx::tma_load_2d_pair(amap, &full_bar[stage], sa, ka, m0);
