@@ -437,6 +437,19 @@ def test_argmax_agreement_with_real_margins(enc_syn):
     assert relmax(mpv, pv) <= BF16_TOL and relmax(mgpn, gpn) <= BF16_TOL
 
 
+def test_forward_features_equals_forward(enc_syn):
+    """`forward_features` (the entry the cross-epoch feature cache uses) is `forward` minus the backbones."""
+    m = S.FCGGNN(enc_syn, 256, backbone=None).cuda().eval()
+    fv, fn, gt_verb, _ = [x.cuda() for x in make_batch(enc_syn, 19, 256, seed=4)]
+    with torch.no_grad():
+        a = m(fv, gt_verb, img_nouns=fn)
+        b = m.forward_features(fv, fn, gt_verb)
+        ev, en = m.extract_features(fv, fn)
+    assert torch.equal(ev, fv) and torch.equal(en, fn)              # Identity backbones
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
 def test_fp32_mode_is_forward_only(enc_syn):
     m = S.FCGGNN(enc_syn, 256, backbone=None, precision="fp32").cuda()
     x = torch.rand(4, 256, device="cuda")
