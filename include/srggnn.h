@@ -148,16 +148,23 @@ int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t
                   const float* batch_total, float* loss, float* dlogits, float grad_scale, const float* stats,
                   void* stream);
 
-/* Backward of the two losses as its own pass: dlogits = grad_scale * (*grad_out) * dLoss/dlogits, where grad_out is
- * the DEVICE scalar autograd hands to the loss node (nullable = 1).  With these, the forward calls can be given
- * dlogits = NULL (they then only read the target logits when `stats` is available) and no separate scaling pass over
- * the [rows, ldl] gradient is needed. */
+/* Backward of the two losses as its own pass: grad_scale * (*grad_out) * dLoss/dlogits, where grad_out is the DEVICE
+ * scalar autograd hands to the loss node (nullable = 1).  With these, the forward calls can be given dlogits = NULL (they
+ * then only read the target logits when `stats` is available) and no separate scaling pass over the [rows, ldl]
+ * gradient is needed.  The gradient goes to ONE of two places:
+ *   dlogits      : fp32 [rows, ldl] (a caller that wants the gradient as a tensor), or
+ *   dlogits_bf16 : the zero-padded bf16 [rows, padded classes] operand the classifier's backward GEMMs read, i.e. the
+ *                  address `workspace + srg_workspace_dlogits_offset(...)` of the forward call that produced the logits
+ *                  (accumulate = 1: added to what is there, for a second loss on the same logits).  The fp32 gradient
+ *                  is then never written or re-read; srg_nouns_backward / srg_verb_backward are told with
+ *                  dlogits_in_workspace = 1. */
 int srg_nouns_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_nouns, int B,
                             const float* counts, const float* grad_out, float grad_scale, float* dlogits,
-                            const float* stats, void* stream);
+                            void* dlogits_bf16, int accumulate, const float* stats, void* stream);
 int srg_verb_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B,
                            float inv_batch, const float* batch_total, const float* grad_out, float grad_scale,
-                           float* dlogits, const float* stats, void* stream);
+                           float* dlogits, void* dlogits_bf16, int accumulate, const float* stats, void* stream);
+size_t srg_workspace_dlogits_offset(srg_handle* h, int mode, int B, const void* workspace);
 
 /* `stats` (nullable) of the two loss calls: the per-column-tile (row max, row sum-exp) pairs the classifier GEMM of the
  * matching forward call left in its workspace, at this byte offset; with them the loss reads each logits row once
@@ -167,14 +174,16 @@ size_t srg_workspace_stats_offset(srg_handle* h, int mode, int B, int precision,
 
 /* autograd backward of srg_nouns_forward / srg_verb_forward (sr.py:76-79).  `workspace` must be the one used by the
  * matching forward call with save_for_backward = 1, and the dropout arguments must be that call's (the seed scalar
- * must still hold the same value).  dlogits: fp32 [rows, ldl].  Gradients accumulate into `g`. */
-int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const float* feat, const int64_t* verb, int B,
-                       const float* role_emb, const float* verb_emb, const uint8_t* keep, float drop_p,
-                       const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
+ * must still hold the same value).  The gradient of the logits: dlogits fp32 [rows, ldl] (nullable), and / or
+ * dlogits_in_workspace = 1 when srg_*_loss_backward already wrote it into the workspace as bf16 (both: their sum).
+ * Gradients accumulate into `g`. */
+int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, int dlogits_in_workspace, const float* feat,
+                       const int64_t* verb, int B, const float* role_emb, const float* verb_emb, const uint8_t* keep,
+                       float drop_p, const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
                        size_t workspace_bytes, void* stream);
-int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int B, const uint8_t* keep, float drop_p,
-                      const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
-                      size_t workspace_bytes, void* stream);
+int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int dlogits_in_workspace, int B,
+                      const uint8_t* keep, float drop_p, const int64_t* drop_seed, int64_t drop_stream,
+                      const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Deferred chain rule.  The verb node and the role graph share one GGNN (model.py:28-35, 226), so one training step
  * (sr.py:63-79) calls both backward functions with the same weights.  Their gradients w.r.t. the message-side weights

@@ -46,12 +46,13 @@ SIGNATURES = {
     "srg_count_targets": (_i, [_vp, _vp, _i, _vp, _vp]),
     "srg_nouns_loss": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp]),
     "srg_verb_loss": (_i, [_vp, _vp, _i64, _vp, _i, _f, _vp, _vp, _vp, _f, _vp, _vp]),
-    "srg_nouns_loss_backward": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp]),
-    "srg_verb_loss_backward": (_i, [_vp, _vp, _i64, _vp, _i, _f, _vp, _vp, _f, _vp, _vp, _vp]),
+    "srg_nouns_loss_backward": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _f, _vp, _vp, _i, _vp, _vp]),
+    "srg_verb_loss_backward": (_i, [_vp, _vp, _i64, _vp, _i, _f, _vp, _vp, _f, _vp, _vp, _i, _vp, _vp]),
     "srg_workspace_stats_offset": (_sz, [_vp, _i, _i, _i, _i, _vp]),
-    "srg_nouns_backward": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _c.POINTER(SrgGrads), _vp,
-                                _sz, _vp]),
-    "srg_verb_backward": (_i, [_vp, _vp, _i64, _i, _vp, _f, _vp, _i64, _c.POINTER(SrgGrads), _vp, _sz, _vp]),
+    "srg_workspace_dlogits_offset": (_sz, [_vp, _i, _i, _vp]),
+    "srg_nouns_backward": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _c.POINTER(SrgGrads),
+                                _vp, _sz, _vp]),
+    "srg_verb_backward": (_i, [_vp, _vp, _i64, _i, _i, _vp, _f, _vp, _i64, _c.POINTER(SrgGrads), _vp, _sz, _vp]),
     "srg_set_deferred_chain": (_i, [_vp, _i, _vp]),
     "srg_chain_finalize": (_i, [_vp, _c.POINTER(SrgGrads), _vp]),
     "srg_clip_adamax": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp, _vp]),

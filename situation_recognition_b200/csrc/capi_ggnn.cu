@@ -435,7 +435,9 @@ int chain_rule(srg_handle* h, const float* G_P, bf16* G_Pb, const float* s_all, 
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, int64_t ldl, int B,
+// dlogits (nullable) fp32 [Mfull, ldl]; dlb_ready: the bf16 gradient operand pb.dlb already holds a gradient written by
+// the loss kernels (srg_*_loss_backward with dlogits_bf16); both given: their sum.
+int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, int64_t ldl, int dlb_ready, int B,
                   const DropSpec& ds, const srg_grads* g, cudaStream_t s) {
   const int D = h->D, T = h->T, M = pb.M, Mf = pb.Mfull, R = h->R;
   const int ncls = (mode == SRG_MODE_NOUN) ? h->L : h->V;
@@ -462,7 +464,8 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
   }
 
   // ---- classifier (model.py:105-111,152,168): one row per node slot
-  SRG_TRY(launch_cast_pad(dlogits, ldl, Mf, ncls, npad, pb.dlb, s));
+  SRG_CHECK(dlogits != nullptr || dlb_ready, "backward: no gradient of the logits was given");
+  if (dlogits != nullptr) SRG_TRY(launch_cast_pad(dlogits, ldl, Mf, ncls, npad, pb.dlb, dlb_ready ? 1 : 0, s));
   SRG_TRY(launch_colsum(pb.dlb, npad, Mf, ncls, gbc, 1.f, nullptr, 0.f, s));
   SRG_TRY(wgrad(h, pb.dlb, npad, ncls, x, D, 1, Mf, Mf, nullptr, gWc, s));
   {
@@ -473,9 +476,6 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
     p.epi = EPI_STORE_F32;
     p.io[0] = mat(gathered ? pb.dx : pb.dh, Mf, D, D, DT_F32);
     SRG_TRY(run_gemm(p, h->dev, s));
-    // back through the dropout and the slot -> state-row gather: the pad slots of all images add up in the shared pad row
-    if (gathered) SRG_TRY(launch_classifier_input_bwd(pb.dx, pb.rm, (mode == SRG_MODE_NOUN) ? B : Mf,
-                                                      (mode == SRG_MODE_NOUN) ? R : 1, D, ds, pb.dh, s));
   }
 
   // dL/dh' of the last step comes from the classifier; from there on the GRU-gate derivatives of step t-1 are fused
@@ -483,8 +483,27 @@ int path_backward(srg_handle* h, int mode, PathBufs& pb, const float* dlogits, i
   // dpre_of(t) = [dpre_h | dpre_z | dpre_r] of step t as column blocks of one [M, 3D] matrix.
   float* dh_acc = pb.dh_acc;
   auto dpre_of = [&](int t) { return pb.dpre_all + static_cast<size_t>(t) * M * ld3; };
-  SRG_TRY(launch_gru_bwd_pre_ld(pb.dh, static_cast<const bf16*>(pb.st[T - 1].z), pb.st[T - 1].hc, pb.hb_hi[T - 1], M,
-                                rows_dev, D, dpre_of(T - 1) + D, dpre_of(T - 1), ld3, dh_acc, s));
+  if (gathered) {
+    // back through the dropout and the slot -> state-row gather, with the gate derivatives of the last step applied in
+    // the same pass for every row that has exactly one slot; the pad slots of all images add up in the shared pad row,
+    // whose derivatives (and the zero rows up to the tile boundary) follow in a launch over those few rows
+    GruPre gp;
+    gp.z = static_cast<const bf16*>(pb.st[T - 1].z);
+    gp.hc = pb.st[T - 1].hc;
+    gp.h = pb.hb_hi[T - 1];
+    gp.dpre_z = dpre_of(T - 1) + D;
+    gp.dpre_h = dpre_of(T - 1);
+    gp.ld_out = ld3;
+    gp.dh_acc = dh_acc;
+    SRG_TRY(launch_classifier_input_bwd(pb.dx, pb.rm, (mode == SRG_MODE_NOUN) ? B : Mf, (mode == SRG_MODE_NOUN) ? R : 1,
+                                        D, ds, pb.dh, gp, s));
+    if (mapped)
+      SRG_TRY(launch_gru_bwd_pre_ld(pb.dh, gp.z, gp.hc, gp.h, 256, rows_dev, pb.rm.meta + 1, D, gp.dpre_z, gp.dpre_h,
+                                    ld3, dh_acc, s));
+  } else {
+    SRG_TRY(launch_gru_bwd_pre_ld(pb.dh, static_cast<const bf16*>(pb.st[T - 1].z), pb.st[T - 1].hc, pb.hb_hi[T - 1], M,
+                                  nullptr, nullptr, D, dpre_of(T - 1) + D, dpre_of(T - 1), ld3, dh_acc, s));
+  }
   for (int t = T - 1; t >= 0; --t) {
     StepBufs& st = pb.st[t];
     bf16* dp = dpre_of(t);
@@ -806,6 +825,12 @@ size_t srg_workspace_stats_offset(srg_handle* h, int mode, int B, int precision,
   return static_cast<size_t>(reinterpret_cast<const uint8_t*>(pb.stats) - static_cast<const uint8_t*>(workspace));
 }
 
+size_t srg_workspace_dlogits_offset(srg_handle* h, int mode, int B, const void* workspace) {
+  if (!h || B <= 0 || !workspace) return 0;
+  PathBufs pb = carve(h, mode, B, SRG_PREC_BF16, 1, const_cast<void*>(workspace), mode == SRG_MODE_NOUN);
+  return static_cast<size_t>(reinterpret_cast<const uint8_t*>(pb.dlb) - static_cast<const uint8_t*>(workspace));
+}
+
 size_t srg_workspace_bytes(srg_handle* h, int mode, int B, int precision, int save_for_backward) {
   if (!h || B <= 0) return 0;
   // role-graph paths: the row-mapped layout of srg_nouns_* is the larger one (srg_ggnn_forward uses dense rows)
@@ -894,18 +919,19 @@ int srg_nouns_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_
   SRG_CHECK(h && logits && gt_nouns && counts && loss, "srg_nouns_loss: null argument");
   SRG_CHECK(ldl >= h->L, "srg_nouns_loss: ldl %lld < n_labels %d", (long long)ldl, h->L);
   return launch_nouns_ce(logits, ldl, h->L, gt_nouns, B, h->R, counts, loss, dlogits, grad_scale, nullptr, stats,
-                         h->Lpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
+                         h->Lpad / ((h->cg == 2) ? 256 : 128), nullptr, 0, 0, static_cast<cudaStream_t>(stream));
 }
 
 int srg_nouns_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_nouns, int B,
                             const float* counts, const float* grad_out, float grad_scale, float* dlogits,
-                            const float* stats, void* stream) {
+                            void* dlogits_bf16, int accumulate, const float* stats, void* stream) {
   SRG_CHECK(h != nullptr, "srg_nouns_loss_backward: null handle");
   DeviceGuard guard_(h->device);
-  SRG_CHECK(h && logits && gt_nouns && counts && dlogits, "srg_nouns_loss_backward: null argument");
+  SRG_CHECK(h && logits && gt_nouns && counts && (dlogits || dlogits_bf16), "srg_nouns_loss_backward: null argument");
   SRG_CHECK(ldl >= h->L, "srg_nouns_loss_backward: ldl %lld < n_labels %d", (long long)ldl, h->L);
   return launch_nouns_ce(logits, ldl, h->L, gt_nouns, B, h->R, counts, nullptr, dlogits, grad_scale, grad_out, stats,
-                         h->Lpad / ((h->cg == 2) ? 256 : 128), static_cast<cudaStream_t>(stream));
+                         h->Lpad / ((h->cg == 2) ? 256 : 128), static_cast<bf16*>(dlogits_bf16), h->Lpad, accumulate,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B, float inv_batch,
@@ -916,18 +942,20 @@ int srg_verb_loss(srg_handle* h, const float* logits, int64_t ldl, const int64_t
   SRG_CHECK(h && logits && gt_verb && loss, "srg_verb_loss: null argument");
   SRG_CHECK(ldl >= h->V, "srg_verb_loss: ldl %lld < n_verbs %d", (long long)ldl, h->V);
   return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, loss, dlogits, grad_scale, nullptr, stats,
-                        h->Vpad / ((h->cg == 2) ? 256 : 128), batch_total, static_cast<cudaStream_t>(stream));
+                        h->Vpad / ((h->cg == 2) ? 256 : 128), batch_total, nullptr, 0, 0,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int srg_verb_loss_backward(srg_handle* h, const float* logits, int64_t ldl, const int64_t* gt_verb, int B,
                            float inv_batch, const float* batch_total, const float* grad_out, float grad_scale,
-                           float* dlogits, const float* stats, void* stream) {
+                           float* dlogits, void* dlogits_bf16, int accumulate, const float* stats, void* stream) {
   SRG_CHECK(h != nullptr, "srg_verb_loss_backward: null handle");
   DeviceGuard guard_(h->device);
-  SRG_CHECK(h && logits && gt_verb && dlogits, "srg_verb_loss_backward: null argument");
+  SRG_CHECK(h && logits && gt_verb && (dlogits || dlogits_bf16), "srg_verb_loss_backward: null argument");
   SRG_CHECK(ldl >= h->V, "srg_verb_loss_backward: ldl %lld < n_verbs %d", (long long)ldl, h->V);
   return launch_verb_ce(logits, ldl, h->V, gt_verb, B, inv_batch, nullptr, dlogits, grad_scale, grad_out, stats,
-                        h->Vpad / ((h->cg == 2) ? 256 : 128), batch_total, static_cast<cudaStream_t>(stream));
+                        h->Vpad / ((h->cg == 2) ? 256 : 128), batch_total, static_cast<bf16*>(dlogits_bf16), h->Vpad,
+                        accumulate, static_cast<cudaStream_t>(stream));
 }
 
 int srg_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, float lr, float beta1,
@@ -982,40 +1010,42 @@ int srg_chain_finalize(srg_handle* h, const srg_grads* g, void* stream) {
   return SRG_OK;
 }
 
-int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, const float* feat, const int64_t* verb, int B,
-                       const float* role_emb, const float* verb_emb, const uint8_t* keep, float drop_p,
-                       const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
+int srg_nouns_backward(srg_handle* h, const float* dlogits, int64_t ldl, int dlogits_in_workspace, const float* feat,
+                       const int64_t* verb, int B, const float* role_emb, const float* verb_emb, const uint8_t* keep,
+                       float drop_p, const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
                        size_t workspace_bytes, void* stream) {
   SRG_CHECK(h != nullptr, "srg_nouns_backward: null handle");
   DeviceGuard guard_(h->device);
   PathBufs pb;
   SRG_TRY(check_ws(h, SRG_MODE_NOUN, B, SRG_PREC_BF16, 1, workspace, workspace_bytes, &pb, true));
   SRG_CHECK(h->packed_prec == SRG_PREC_BF16, "backward needs bf16-packed weights");
-  SRG_CHECK(dlogits && feat && verb && role_emb && verb_emb && g, "srg_nouns_backward: null argument");
-  SRG_CHECK(ldl >= h->L, "srg_nouns_backward: ldl %lld < n_labels %d", (long long)ldl, h->L);
+  SRG_CHECK((dlogits || dlogits_in_workspace) && feat && verb && role_emb && verb_emb && g,
+            "srg_nouns_backward: null argument");
+  SRG_CHECK(dlogits == nullptr || ldl >= h->L, "srg_nouns_backward: ldl %lld < n_labels %d", (long long)ldl, h->L);
   DropSpec ds;
   SRG_TRY(make_drop(keep, drop_p, drop_seed, drop_stream, &ds));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  SRG_TRY(path_backward(h, SRG_MODE_NOUN, pb, dlogits, ldl, B, ds, g, s));
+  SRG_TRY(path_backward(h, SRG_MODE_NOUN, pb, dlogits, ldl, dlogits_in_workspace, B, ds, g, s));
   if (g->role_emb != nullptr && g->verb_emb != nullptr)
     SRG_TRY(launch_node_init_bwd(pb.dh, pb.hb_hi[0], feat, role_emb, verb_emb, verb, h->d_verb2roles, h->V, h->n_roles, B,
                                  h->R, h->D, pb.rm, g->role_emb, g->verb_emb, s));
   return SRG_OK;
 }
 
-int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int B, const uint8_t* keep, float drop_p,
-                      const int64_t* drop_seed, int64_t drop_stream, const srg_grads* g, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+int srg_verb_backward(srg_handle* h, const float* dlogits, int64_t ldl, int dlogits_in_workspace, int B,
+                      const uint8_t* keep, float drop_p, const int64_t* drop_seed, int64_t drop_stream,
+                      const srg_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
   SRG_CHECK(h != nullptr, "srg_verb_backward: null handle");
   DeviceGuard guard_(h->device);
   PathBufs pb;
   SRG_TRY(check_ws(h, SRG_MODE_VERB, B, SRG_PREC_BF16, 1, workspace, workspace_bytes, &pb, false));
   SRG_CHECK(h->packed_prec == SRG_PREC_BF16, "backward needs bf16-packed weights");
-  SRG_CHECK(dlogits && g, "srg_verb_backward: null argument");
-  SRG_CHECK(ldl >= h->V, "srg_verb_backward: ldl %lld < n_verbs %d", (long long)ldl, h->V);
+  SRG_CHECK((dlogits || dlogits_in_workspace) && g, "srg_verb_backward: null argument");
+  SRG_CHECK(dlogits == nullptr || ldl >= h->V, "srg_verb_backward: ldl %lld < n_verbs %d", (long long)ldl, h->V);
   DropSpec ds;
   SRG_TRY(make_drop(keep, drop_p, drop_seed, drop_stream, &ds));
-  return path_backward(h, SRG_MODE_VERB, pb, dlogits, ldl, B, ds, g, static_cast<cudaStream_t>(stream));
+  return path_backward(h, SRG_MODE_VERB, pb, dlogits, ldl, dlogits_in_workspace, B, ds, g,
+                       static_cast<cudaStream_t>(stream));
 }
 
 #ifdef SRG_EPI_TIMING

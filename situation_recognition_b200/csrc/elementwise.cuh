@@ -53,8 +53,20 @@ int launch_aggregate_t_rows(const bf16* da, const bf16* e, RowMap rm, int B, int
 // x[row] = dropout(h32[row of slot `row` under rm]) for all `rows` node slots -> bf16 hi (+ mid, lo)
 int launch_classifier_input(const float* h32, RowMap rm, int R, int64_t rows, int D, DropSpec ds, bf16* x_hi,
                             bf16* x_mid, bf16* x_lo, cudaStream_t s);
-// dh[row under rm] = dropout'(dx[slot]) with all pad slots summed into the shared pad row
-int launch_classifier_input_bwd(const float* dx, RowMap rm, int B, int R, int D, DropSpec ds, float* dh,
+// GRU-gate derivatives of the LAST propagation step, fused into launch_classifier_input_bwd for the rows it writes
+// (z == nullptr: off): dpre_z = g (hc - h) z (1 - z), dpre_h = g z (1 - hc^2), dh_acc = g (1 - z) with g = dL/dh'
+struct GruPre {
+  const bf16* z = nullptr;
+  const bf16* hc = nullptr;
+  const bf16* h = nullptr;
+  bf16* dpre_z = nullptr;
+  bf16* dpre_h = nullptr;
+  int64_t ld_out = 0;
+  float* dh_acc = nullptr;
+};
+// dh[row under rm] = dropout'(dx[slot]) with all pad slots summed into the shared pad row; with `gp` the real rows get
+// their gate derivatives instead of dh (launch_gru_bwd_pre_ld then only has to run on the self-loop rows)
+int launch_classifier_input_bwd(const float* dx, RowMap rm, int B, int R, int D, DropSpec ds, float* dh, GruPre gp,
                                 cudaStream_t s);
 // out[rows, D] uint8 = the keep decisions `ds` makes (tests: feeds the oracle the mask the Philox path used)
 int launch_dropout_mask(DropSpec ds, int64_t rows, int D, uint8_t* out, cudaStream_t s);
@@ -85,14 +97,17 @@ int launch_pack_bias(const float* a, const float* b, int n, int n_pad, float* ds
 int launch_count_targets(const int64_t* gt, int B, int R, int ignore_index, float* counts, cudaStream_t s);
 // one warp per logits row; loss and dlogits are both optional; the gradient is scaled by grad_scale and, when
 // gscale_dev is not null, by that device scalar as well
+// dlb (nullable, instead of dlogits): the gradient as the zero-padded bf16 [rows, n_pad] operand of the classifier's
+// backward GEMMs; accumulate: added to what dlb already holds
 int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_t* gt, int B, int R,
                     const float* counts, float* loss, float* dlogits, float grad_scale, const float* gscale_dev,
-                    const float* stats, int stats_tiles, cudaStream_t s);
+                    const float* stats, int stats_tiles, bf16* dlb, int n_pad, int accumulate, cudaStream_t s);
 int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t* gt, int B, float inv_batch,
                    float* loss, float* dlogits, float grad_scale, const float* gscale_dev, const float* stats,
-                   int stats_tiles, const float* batch_total, cudaStream_t s);
+                   int stats_tiles, const float* batch_total, bf16* dlb, int n_pad, int accumulate, cudaStream_t s);
 // fp32 [rows, ld] (first n_valid columns) -> bf16 [rows, n_pad], zero padded
-int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, cudaStream_t s);
+int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, int accumulate,
+                    cudaStream_t s);
 
 // out1[c] (+= scale1 * colsum) , out2[c] (+= scale2 * colsum); X bf16 [rows, ld], first n_cols columns
 int launch_colsum(const bf16* X, int64_t ld, int rows, int n_cols, float* out1, float scale1, float* out2,
@@ -128,9 +143,10 @@ int launch_clip_adamax(float* params, float* grads, float* exp_avg, float* exp_i
                        float beta2, float eps, float max_norm, float* norm_sq, float* step, cudaStream_t s);
 
 // GRU backward prologue writing into column blocks of a wider matrix (leading dimension ld_out elements)
-// rows_dev (nullable): device count of rows, overrides `rows` (which then only sizes the grid)
+// rows [row0, rows): rows_dev / row0_dev (nullable) are device-resident overrides (`rows` then only sizes the grid)
 int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int rows, const int* rows_dev,
-                          int D, bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc, cudaStream_t s);
+                          const int* row0_dev, int D, bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc,
+                          cudaStream_t s);
 // y[o] = sum_k W[o,k] x[k]                       (fp32, W row-major [rows, cols])
 int launch_matvec(const float* W, const float* x, int rows, int cols, float* y, cudaStream_t s);
 // y[k] += sum_x sum_o W_x[o,k] s[x*rows + o]    (three [rows, cols] matrices in one launch; null W_x skipped)

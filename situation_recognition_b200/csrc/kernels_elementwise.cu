@@ -368,7 +368,7 @@ __global__ void k_zero_self_rows(float* __restrict__ x, RowMap rm, int D) {
 // the shared pad row (the backward pass of one state row feeding many classifier rows), which k_zero_self_rows cleared.
 // grid = (column chunks, image slabs); rm.cnt == nullptr: one row per "image", R = 1 (verb node path).
 __global__ void k_classifier_input_bwd(const float* __restrict__ dx, RowMap rm, int B, int R, int D, DropSpec ds,
-                                       float* __restrict__ dh) {
+                                       float* __restrict__ dh, GruPre gp) {
   const int D8 = D / 8;
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
   if (c8 >= D8) return;
@@ -386,7 +386,34 @@ __global__ void k_classifier_input_bwd(const float* __restrict__ dx, RowMap rm, 
       float v[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = ((m >> i) & 1u) ? v[i] * sc : 0.f;
-      if (r < L) {
+      if (r < L && gp.z != nullptr) {
+        // v = dL/dh' of the last propagation step on this state row: its GRU-gate derivatives right here, so dL/dh'
+        // is never written (k_gru_bwd_pre_ld only runs on the few self-loop rows, whose dL/dh' is a sum over slots)
+        const int64_t o = (base + r) * D + c8 * 8;
+        const uint4 zz = *reinterpret_cast<const uint4*>(gp.z + o), cc = *reinterpret_cast<const uint4*>(gp.hc + o),
+                    hh = *reinterpret_cast<const uint4*>(gp.h + o);
+        const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w}, cw[4] = {cc.x, cc.y, cc.z, cc.w}, hw[4] = {hh.x, hh.y, hh.z, hh.w};
+        float dz[8], dc[8], da[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float zv = (i & 1) ? bf16_hi_f(zw[i >> 1]) : bf16_lo_f(zw[i >> 1]);
+          const float cv = (i & 1) ? bf16_hi_f(cw[i >> 1]) : bf16_lo_f(cw[i >> 1]);
+          const float hv = (i & 1) ? bf16_hi_f(hw[i >> 1]) : bf16_lo_f(hw[i >> 1]);
+          dz[i] = v[i] * (cv - hv) * zv * (1.f - zv);
+          dc[i] = v[i] * zv * (1.f - cv * cv);
+          da[i] = v[i] * (1.f - zv);
+        }
+        const int64_t oo = (base + r) * gp.ld_out + c8 * 8;
+        uint4 pz, ph;
+        const uint2 z0 = pack4_bf16(dz[0], dz[1], dz[2], dz[3]), z1 = pack4_bf16(dz[4], dz[5], dz[6], dz[7]);
+        const uint2 c0 = pack4_bf16(dc[0], dc[1], dc[2], dc[3]), c1 = pack4_bf16(dc[4], dc[5], dc[6], dc[7]);
+        pz.x = z0.x; pz.y = z0.y; pz.z = z1.x; pz.w = z1.y;
+        ph.x = c0.x; ph.y = c0.y; ph.z = c1.x; ph.w = c1.y;
+        *reinterpret_cast<uint4*>(gp.dpre_z + oo) = pz;
+        *reinterpret_cast<uint4*>(gp.dpre_h + oo) = ph;
+        *reinterpret_cast<float4*>(gp.dh_acc + o) = make_float4(da[0], da[1], da[2], da[3]);
+        *reinterpret_cast<float4*>(gp.dh_acc + o + 4) = make_float4(da[4], da[5], da[6], da[7]);
+      } else if (r < L) {
         float* dp = dh + (base + r) * D + c8 * 8;
         *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(dp + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -474,7 +501,11 @@ __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, i
                                 const float* __restrict__ counts, float inv_fixed, float* __restrict__ loss,
                                 float* __restrict__ dlogits, float grad_scale, const float* __restrict__ gscale_dev,
                                 const float2* __restrict__ stats, int stats_tiles,
-                                const float* __restrict__ total_dev) {
+                                const float* __restrict__ total_dev, bf16* __restrict__ dlb, int64_t ld_b, int n_pad,
+                                int accumulate) {
+  // dlb (nullable): the gradient goes out as the zero-padded bf16 [rows, n_pad] operand of the classifier's backward
+  // GEMMs instead of (not in addition to) the fp32 dlogits -- the fp32 gradient is then never written or re-read
+  // (accumulate: add to what dlb holds, for a second loss on the same logits)
   __shared__ float s_loss[kThreads / 32];
   // total_dev: device scalar holding the GLOBAL number of rows the mean is taken over (all-reduced by the caller when
   // the batch is sharded unevenly); overrides inv_fixed
@@ -501,7 +532,7 @@ __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, i
       }
       wsum += w[a];
     }
-    if (wsum == 0.f && dlogits == nullptr) continue;  // fully ignored row contributes nothing
+    if (wsum == 0.f && dlogits == nullptr && dlb == nullptr) continue;  // fully ignored row contributes nothing
     float mx = -INFINITY, se = 0.f;
     if (stats != nullptr) {
       // the classifier GEMM already reduced every 128/256-column tile of this row to (max, sum exp(x - max)):
@@ -522,7 +553,41 @@ __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, i
       for (int a = 0; a < NT; ++a)
         if (w[a] != 0.f) my_loss += w[a] * (lse - lr[tgt[a]]);
     }
-    if (dlogits != nullptr) {
+    if (dlb != nullptr) {
+      bf16* br = dlb + static_cast<int64_t>(row) * ld_b;
+      const float inv_se = 1.0f / se;
+      const float ws = wsum * grad_scale;
+      // n_pad is a multiple of 128 here (the classifier pads to 256 columns); logits rows are 16-byte aligned
+      for (int c = lane * 4; c < n_pad; c += 128) {
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < n_classes && wsum != 0.f) {
+          float x[4];
+          if (c + 4 <= ldl && ((reinterpret_cast<uintptr_t>(lr) & 15) == 0) && (ldl & 3) == 0) {
+            const float4 v = *reinterpret_cast<const float4*>(lr + c);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = (c + k < n_classes) ? lr[c + k] : 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (c + k < n_classes) {
+              float v = ws * __expf(x[k] - mx) * inv_se;
+#pragma unroll
+              for (int a = 0; a < NT; ++a)
+                if (w[a] != 0.f && tgt[a] == c + k) v -= w[a] * grad_scale;
+              g[k] = v;
+            }
+          }
+        }
+        uint2* dst = reinterpret_cast<uint2*>(br + c);
+        if (accumulate) {
+          const uint2 old = *dst;
+          g[0] += bf16_lo_f(old.x); g[1] += bf16_hi_f(old.x); g[2] += bf16_lo_f(old.y); g[3] += bf16_hi_f(old.y);
+        }
+        *dst = pack4_bf16(g[0], g[1], g[2], g[3]);
+      }
+    } else if (dlogits != nullptr) {
       float* dr = dlogits + static_cast<int64_t>(row) * ldl;
       const float inv_se = 1.0f / se;
       const float ws = wsum * grad_scale;
@@ -569,7 +634,7 @@ __global__ void k_cross_entropy(const float* __restrict__ logits, int64_t ldl, i
 }
 
 __global__ void k_cast_pad(const float* __restrict__ src, int64_t ld, int rows, int n_valid, int n_pad,
-                           bf16* __restrict__ dst) {
+                           bf16* __restrict__ dst, int accumulate) {
   // eight columns per thread: two 16-byte loads, one 16-byte store (n_pad is a multiple of 8; ld a multiple of 4)
   const int c8 = n_pad / 8;
   const int64_t total = static_cast<int64_t>(rows) * c8;
@@ -590,10 +655,16 @@ __global__ void k_cast_pad(const float* __restrict__ src, int64_t ld, int rows, 
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (c + k >= n_valid) v[k] = 0.f;
+    uint4* dp = reinterpret_cast<uint4*>(dst + static_cast<int64_t>(r) * n_pad + c);
+    if (accumulate) {   // on top of a gradient a loss kernel already wrote there as bf16
+      const uint4 old = *dp;
+      v[0] += bf16_lo_f(old.x); v[1] += bf16_hi_f(old.x); v[2] += bf16_lo_f(old.y); v[3] += bf16_hi_f(old.y);
+      v[4] += bf16_lo_f(old.z); v[5] += bf16_hi_f(old.z); v[6] += bf16_lo_f(old.w); v[7] += bf16_hi_f(old.w);
+    }
     uint4 o;
     const uint2 lo = pack4_bf16(v[0], v[1], v[2], v[3]), hi = pack4_bf16(v[4], v[5], v[6], v[7]);
     o.x = lo.x; o.y = lo.y; o.z = hi.x; o.w = hi.y;
-    *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(r) * n_pad + c) = o;
+    *dp = o;
   }
 }
 
@@ -793,15 +864,17 @@ __global__ void k_colsum_multi(ColsumJobs jobs, int64_t ld, int rows, const int*
 }
 
 __global__ void k_gru_bwd_pre_ld(const float* __restrict__ dh, const bf16* __restrict__ z, const bf16* __restrict__ hc,
-                                 const bf16* __restrict__ h, int rows, const int* __restrict__ rows_dev, int D,
-                                 bf16* __restrict__ dpre_z, bf16* __restrict__ dpre_h, int64_t ld_out,
-                                 float* __restrict__ dh_acc) {
+                                 const bf16* __restrict__ h, int rows, const int* __restrict__ rows_dev,
+                                 const int* __restrict__ row0_dev, int D, bf16* __restrict__ dpre_z,
+                                 bf16* __restrict__ dpre_h, int64_t ld_out, float* __restrict__ dh_acc) {
+  // rows [row0, rows): both ends may live on the device (the self-loop rows of a compact role-graph path)
   if (rows_dev != nullptr) rows = __ldg(rows_dev);
+  const int row0 = (row0_dev != nullptr) ? __ldg(row0_dev) : 0;
   const int D4 = D / 4;
-  const int64_t total = static_cast<int64_t>(rows) * D4;
+  const int64_t total = static_cast<int64_t>(rows - row0) * D4;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t row = t / D4;
+    const int64_t row = row0 + t / D4;
     const int col = static_cast<int>(t % D4) * 4;
     const int64_t i = row * D + col;
     const float4 g = *reinterpret_cast<const float4*>(dh + i);
@@ -1026,7 +1099,7 @@ int launch_count_targets(const int64_t* gt, int B, int R, int ignore_index, floa
 
 int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_t* gt, int B, int R,
                     const float* counts, float* loss, float* dlogits, float grad_scale, const float* gscale_dev,
-                    const float* stats, int stats_tiles, cudaStream_t s) {
+                    const float* stats, int stats_tiles, bf16* dlb, int n_pad, int accumulate, cudaStream_t s) {
   const int rows = B * R;
   if (rows <= 0) return SRG_OK;
   int blocks = (rows + 7) / 8;
@@ -1034,29 +1107,33 @@ int launch_nouns_ce(const float* logits, int64_t ldl, int n_labels, const int64_
   if (stats_tiles > 32) stats = nullptr;
   k_cross_entropy<3><<<blocks, kThreads, 0, s>>>(logits, ldl, n_labels, rows, gt, R, n_labels, counts, 0.f, loss,
                                                 dlogits, grad_scale, gscale_dev,
-                                                reinterpret_cast<const float2*>(stats), stats_tiles, nullptr);
+                                                reinterpret_cast<const float2*>(stats), stats_tiles, nullptr, dlb, n_pad,
+                                                n_pad, accumulate);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
 int launch_verb_ce(const float* logits, int64_t ldl, int n_verbs, const int64_t* gt, int B, float inv_batch,
                    float* loss, float* dlogits, float grad_scale, const float* gscale_dev, const float* stats,
-                   int stats_tiles, const float* batch_total, cudaStream_t s) {
+                   int stats_tiles, const float* batch_total, bf16* dlb, int n_pad, int accumulate, cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   int blocks = (B + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (stats_tiles > 32) stats = nullptr;
   k_cross_entropy<1><<<blocks, kThreads, 0, s>>>(logits, ldl, n_verbs, B, gt, 1, -100, nullptr, inv_batch, loss,
                                                 dlogits, grad_scale, gscale_dev,
-                                                reinterpret_cast<const float2*>(stats), stats_tiles, batch_total);
+                                                reinterpret_cast<const float2*>(stats), stats_tiles, batch_total, dlb,
+                                                n_pad, n_pad, accumulate);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
 
-int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, cudaStream_t s) {
+int launch_cast_pad(const float* src, int64_t ld, int rows, int n_valid, int n_pad, bf16* dst, int accumulate,
+                    cudaStream_t s) {
   if (rows <= 0) return SRG_OK;
   if (n_pad % 8 != 0) return set_error(SRG_ERR_ARG, "cast_pad: padded width %d must be a multiple of 8", n_pad);
-  k_cast_pad<<<grid_for(static_cast<int64_t>(rows) * n_pad / 8), kThreads, 0, s>>>(src, ld, rows, n_valid, n_pad, dst);
+  k_cast_pad<<<grid_for(static_cast<int64_t>(rows) * n_pad / 8), kThreads, 0, s>>>(src, ld, rows, n_valid, n_pad, dst,
+                                                                                   accumulate);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
@@ -1120,7 +1197,7 @@ int launch_classifier_input(const float* h32, RowMap rm, int R, int64_t rows, in
   return SRG_OK;
 }
 
-int launch_classifier_input_bwd(const float* dx, RowMap rm, int B, int R, int D, DropSpec ds, float* dh,
+int launch_classifier_input_bwd(const float* dx, RowMap rm, int B, int R, int D, DropSpec ds, float* dh, GruPre gp,
                                 cudaStream_t s) {
   if (B <= 0) return SRG_OK;
   if (D % 8 != 0) return set_error(SRG_ERR_ARG, "classifier_input_bwd: D=%d must be a multiple of 8", D);
@@ -1135,7 +1212,7 @@ int launch_classifier_input_bwd(const float* dx, RowMap rm, int B, int R, int D,
   if (slabs > B) slabs = B;
   if (slabs < 1) slabs = 1;
   dim3 grid(chunks, slabs);
-  k_classifier_input_bwd<<<grid, threads, 0, s>>>(dx, rm, B, R, D, ds, dh);
+  k_classifier_input_bwd<<<grid, threads, 0, s>>>(dx, rm, B, R, D, ds, dh, gp);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }
@@ -1175,10 +1252,11 @@ int launch_colsum_multi(const ColsumJob* jobs, int n_jobs, int64_t ld, int rows,
 }
 
 int launch_gru_bwd_pre_ld(const float* dh, const bf16* z, const bf16* hc, const bf16* h, int rows, const int* rows_dev,
-                          int D, bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc, cudaStream_t s) {
+                          const int* row0_dev, int D, bf16* dpre_z, bf16* dpre_h, int64_t ld_out, float* dh_acc,
+                          cudaStream_t s) {
   if (rows <= 0) return SRG_OK;
-  k_gru_bwd_pre_ld<<<grid_for(static_cast<int64_t>(rows) * D / 4), kThreads, 0, s>>>(dh, z, hc, h, rows, rows_dev, D,
-                                                                                    dpre_z, dpre_h, ld_out, dh_acc);
+  k_gru_bwd_pre_ld<<<grid_for(static_cast<int64_t>(rows) * D / 4), kThreads, 0, s>>>(
+      dh, z, hc, h, rows, rows_dev, row0_dev, D, dpre_z, dpre_h, ld_out, dh_acc);
   SRG_LAUNCH_CHECK();
   return SRG_OK;
 }

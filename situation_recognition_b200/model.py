@@ -223,6 +223,17 @@ def _grad_struct(named, engine):
 _GGNN_FIELDS = _lib._PARAM_FIELDS[:14]
 
 
+class _GradTap:
+    """Where the loss kernels put d(loss)/d(logits) for a stage that is waiting for it: the bf16, zero-padded operand
+    buffer of the classifier's backward GEMMs inside the stage's workspace.  `FCGGNN.verb_loss` / `nouns_loss` write
+    there directly when they are applied to the very tensor a `predict_*` call returned, so the fp32 gradient tensor is
+    never materialised (nor re-read and converted).  autograd still orders the two nodes: the stage returns a 1-element
+    `tap` tensor next to the logits, the loss takes it as an input and hands back a (dummy) gradient for it."""
+
+    def __init__(self, ws, ptr):
+        self.ws, self.ptr, self.written = ws, ptr, False
+
+
 class _NounsStage(torch.autograd.Function):
     """predict_nouns minus the backbone (model.py:117-155)."""
 
@@ -249,17 +260,24 @@ class _NounsStage(torch.autograd.Function):
             ctx.direct = model._direct_grads()
             ctx.live = (role_emb, verb_emb) + tuple(params)       # the Parameter objects (for .grad in direct mode)
             ctx.save_for_backward(feat, verb, keep, seed, role_emb, verb_emb, *params)
+            ctx.side = _GradTap(ws, ws.data_ptr() + eng.lib.srg_workspace_dlogits_offset(eng.h, SRG_MODE_NOUN, B,
+                                                                                        _lib.ptr(ws)))
+            ctx.set_materialize_grads(False)
         model._last_stats = _stats_view(eng, ws, SRG_MODE_NOUN, B, prec, need_grad)
-        return logits.view(B, eng.R, eng.Lpad)[:, :, :eng.L]
+        model._last_side = ctx.side if need_grad else None
+        return logits.view(B, eng.R, eng.Lpad)[:, :, :eng.L], torch.zeros(1, dtype=torch.float32, device=feat.device)
 
     @staticmethod
-    def backward(ctx, dlogits):
+    def backward(ctx, dlogits, dtap):
         eng = ctx.eng
+        names = ["role_emb", "verb_emb"] + _GGNN_FIELDS + ["Wc_noun", "bc_noun"]
+        in_ws, ctx.side.written = ctx.side.written, False
+        if dlogits is None and not in_ws:           # nothing downstream produced a gradient for these logits
+            return (None,) * (7 + len(names))
         eng.check_pack_gen(ctx.pack_gen)
         feat, verb, keep, seed, role_emb, verb_emb, *params = ctx.saved_tensors
         B = ctx.B
-        dl, ldl = _padded_grad(dlogits.reshape(B * eng.R, eng.L), eng.Lpad)
-        names = ["role_emb", "verb_emb"] + _GGNN_FIELDS + ["Wc_noun", "bc_noun"]
+        dl, ldl = (None, eng.Lpad) if dlogits is None else _padded_grad(dlogits.reshape(B * eng.R, eng.L), eng.Lpad)
         if ctx.direct:   # flat-buffer mode: the kernels accumulate straight into the (pre-zeroed) .grad views
             grads = {n: p.grad for n, p in zip(names, ctx.live)}
             eng.backward_begin(grads)
@@ -267,7 +285,7 @@ class _NounsStage(torch.autograd.Function):
             grads = {n: torch.zeros_like(p) for n, p in zip(names, (role_emb, verb_emb) + tuple(params))}
             eng.set_deferred(False)
         sg = _grad_struct(grads, eng)
-        _lib.check(eng.lib.srg_nouns_backward(eng.h, _lib.ptr(dl), ldl, _lib.ptr(feat), _lib.ptr(verb), B,
+        _lib.check(eng.lib.srg_nouns_backward(eng.h, _lib.ptr(dl), ldl, int(in_ws), _lib.ptr(feat), _lib.ptr(verb), B,
                                               _lib.ptr(role_emb), _lib.ptr(verb_emb), _lib.ptr(keep), ctx.drop_p,
                                               _lib.ptr(seed), ctx.slot, ctypes.byref(sg), _lib.ptr(ctx.ws),
                                               ctx.ws.numel(), eng.stream()))
@@ -303,17 +321,24 @@ class _VerbStage(torch.autograd.Function):
             ctx.direct = model._direct_grads()
             ctx.live = tuple(params)
             ctx.save_for_backward(keep, seed, *params)
+            ctx.side = _GradTap(ws, ws.data_ptr() + eng.lib.srg_workspace_dlogits_offset(eng.h, SRG_MODE_VERB, B,
+                                                                                        _lib.ptr(ws)))
+            ctx.set_materialize_grads(False)
         model._last_stats = _stats_view(eng, ws, SRG_MODE_VERB, B, prec, need_grad)
-        return logits[:, :eng.V]
+        model._last_side = ctx.side if need_grad else None
+        return logits[:, :eng.V], torch.zeros(1, dtype=torch.float32, device=feat.device)
 
     @staticmethod
-    def backward(ctx, dlogits):
+    def backward(ctx, dlogits, dtap):
         eng = ctx.eng
+        names = _GGNN_FIELDS + ["Wc_verb", "bc_verb"]
+        in_ws, ctx.side.written = ctx.side.written, False
+        if dlogits is None and not in_ws:
+            return (None,) * (6 + len(names))
         eng.check_pack_gen(ctx.pack_gen)
         keep, seed, *params = ctx.saved_tensors
         B = ctx.B
-        dl, ldl = _padded_grad(dlogits.reshape(B, eng.V), eng.Vpad)
-        names = _GGNN_FIELDS + ["Wc_verb", "bc_verb"]
+        dl, ldl = (None, eng.Vpad) if dlogits is None else _padded_grad(dlogits.reshape(B, eng.V), eng.Vpad)
         if ctx.direct:
             grads = {n: p.grad for n, p in zip(names, ctx.live)}
             eng.backward_begin(grads)
@@ -321,7 +346,7 @@ class _VerbStage(torch.autograd.Function):
             grads = {n: torch.zeros_like(p) for n, p in zip(names, params)}
             eng.set_deferred(False)
         sg = _grad_struct(grads, eng)
-        _lib.check(eng.lib.srg_verb_backward(eng.h, _lib.ptr(dl), ldl, B, _lib.ptr(keep), ctx.drop_p, _lib.ptr(seed),
+        _lib.check(eng.lib.srg_verb_backward(eng.h, _lib.ptr(dl), ldl, int(in_ws), B, _lib.ptr(keep), ctx.drop_p, _lib.ptr(seed),
                                              ctx.slot, ctypes.byref(sg), _lib.ptr(ctx.ws), ctx.ws.numel(), eng.stream()))
         ctx.ws = None
         if ctx.direct:
@@ -366,11 +391,11 @@ class _NounsLoss(torch.autograd.Function):
     the incoming d(loss), in one pass over the logits."""
 
     @staticmethod
-    def forward(ctx, model, grad_on, logits, gt_nouns, stats):
+    def forward(ctx, model, grad_on, logits, gt_nouns, stats, tap, side):
         eng = model._engine_for(logits.device)
         x, rows, ld = _rows_view(logits, eng.L)
         if x.data_ptr() != logits.data_ptr():
-            stats = None                           # the logits were copied / converted: the statistics do not apply
+            stats = side = None                    # the logits were copied / converted: neither applies
         B = rows // eng.R
         gt = gt_nouns.detach().to(torch.int64).contiguous()
         # the denominators depend on the targets only: nouns_loss(pred_nouns, gt) and nouns_loss(gt_pred_nouns, gt) of
@@ -389,33 +414,40 @@ class _NounsLoss(torch.autograd.Function):
         _lib.check(eng.lib.srg_nouns_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts), _lib.ptr(loss),
                                           None, 1.0, ctypes.c_void_p(stats[1]) if stats else None,
                                           eng.stream()))
-        if grad_on and ctx.needs_input_grad[2]:
+        if grad_on and (ctx.needs_input_grad[2] or ctx.needs_input_grad[5]):
             ctx.save_for_backward(x, gt, counts)
             ctx.eng, ctx.geom, ctx.shape, ctx.stats = eng, (rows, ld, B), tuple(logits.shape), stats
+            ctx.side = side if (side is not None and ctx.needs_input_grad[5] and ld == eng.Lpad) else None
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         x, gt, counts = ctx.saved_tensors
-        eng, (rows, ld, B), stats = ctx.eng, ctx.geom, ctx.stats
+        eng, (rows, ld, B), stats, side = ctx.eng, ctx.geom, ctx.stats, ctx.side
         gout = gout.detach().to(torch.float32).contiguous()
+        st = ctypes.c_void_p(stats[1]) if stats else None
+        ctx.stats = None
+        if side is not None:     # straight into the stage's bf16 operand buffer; the tap carries the dependency
+            _lib.check(eng.lib.srg_nouns_loss_backward(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts),
+                                                       _lib.ptr(gout), 1.0, None, ctypes.c_void_p(side.ptr),
+                                                       int(side.written), st, eng.stream()))
+            side.written = True
+            return None, None, None, None, None, gout.new_zeros(1), None
         dl = torch.empty(rows, ld, dtype=torch.float32, device=x.device)
         _lib.check(eng.lib.srg_nouns_loss_backward(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), B, _lib.ptr(counts),
-                                                   _lib.ptr(gout), 1.0, _lib.ptr(dl),
-                                                   ctypes.c_void_p(stats[1]) if stats else None, eng.stream()))
-        ctx.stats = None
-        return None, None, dl[:, :eng.L].view(ctx.shape), None, None
+                                                   _lib.ptr(gout), 1.0, _lib.ptr(dl), None, 0, st, eng.stream()))
+        return None, None, dl[:, :eng.L].view(ctx.shape), None, None, None, None
 
 
 class _VerbLoss(torch.autograd.Function):
     """FCGGNN.verb_loss (model.py:182-187); same split between forward and backward as _NounsLoss."""
 
     @staticmethod
-    def forward(ctx, model, grad_on, logits, gt_verb, stats):
+    def forward(ctx, model, grad_on, logits, gt_verb, stats, tap, side):
         eng = model._engine_for(logits.device)
         x, rows, ld = _rows_view(logits, eng.V)
         if x.data_ptr() != logits.data_ptr():
-            stats = None
+            stats = side = None
         gt = gt_verb.detach().to(torch.int64).contiguous()
         loss = torch.zeros((), dtype=torch.float32, device=logits.device)
         # The mean is over the GLOBAL batch (the reference computes the loss on the gathered logits of all replicas,
@@ -431,24 +463,31 @@ class _VerbLoss(torch.autograd.Function):
         _lib.check(eng.lib.srg_verb_loss(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, inv, _lib.ptr(total),
                                          _lib.ptr(loss), None, 1.0, ctypes.c_void_p(stats[1]) if stats else None,
                                          eng.stream()))
-        if grad_on and ctx.needs_input_grad[2]:
+        if grad_on and (ctx.needs_input_grad[2] or ctx.needs_input_grad[5]):
             saved = (x, gt) if total is None else (x, gt, total)
             ctx.save_for_backward(*saved)
             ctx.eng, ctx.geom, ctx.shape, ctx.stats = eng, (rows, ld, inv), tuple(logits.shape), stats
+            ctx.side = side if (side is not None and ctx.needs_input_grad[5] and ld == eng.Vpad) else None
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         x, gt, *rest = ctx.saved_tensors
         total = rest[0] if rest else None
-        eng, (rows, ld, inv), stats = ctx.eng, ctx.geom, ctx.stats
+        eng, (rows, ld, inv), stats, side = ctx.eng, ctx.geom, ctx.stats, ctx.side
         gout = gout.detach().to(torch.float32).contiguous()
+        st = ctypes.c_void_p(stats[1]) if stats else None
+        ctx.stats = None
+        if side is not None:
+            _lib.check(eng.lib.srg_verb_loss_backward(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, inv, _lib.ptr(total),
+                                                      _lib.ptr(gout), 1.0, None, ctypes.c_void_p(side.ptr),
+                                                      int(side.written), st, eng.stream()))
+            side.written = True
+            return None, None, None, None, None, gout.new_zeros(1), None
         dl = torch.empty(rows, ld, dtype=torch.float32, device=x.device)
         _lib.check(eng.lib.srg_verb_loss_backward(eng.h, _lib.ptr(x), ld, _lib.ptr(gt), rows, inv, _lib.ptr(total),
-                                                  _lib.ptr(gout), 1.0, _lib.ptr(dl),
-                                                  ctypes.c_void_p(stats[1]) if stats else None, eng.stream()))
-        ctx.stats = None
-        return None, None, dl[:, :eng.V].view(ctx.shape), None, None
+                                                  _lib.ptr(gout), 1.0, _lib.ptr(dl), None, 0, st, eng.stream()))
+        return None, None, dl[:, :eng.V].view(ctx.shape), None, None, None, None
 
 
 def _has_batchnorm_in_train(module):
@@ -511,6 +550,7 @@ class FCGGNN(nn.Module):
         self.overlap_streams = True      # run the verb path on a side stream (see forward)
         self._flat = None                # parallel.attach(): flat gradient / parameter buffers
         self._last_stats = None
+        self._last_side = None
         self._counts_cache = None        # (key, counts, targets) of the last nouns_loss call
 
     # sr.py accesses model.module.* when CUDA is available (DataParallel wrapper in the reference)
@@ -580,10 +620,11 @@ class FCGGNN(nn.Module):
             raise _lib.SrgError("batch_size %d does not match the features (%d)" % (batch_size, feat.shape[0]))
         keep, seed = self._dropout(_mask_slot, feat.device)
         gt_verb = gt_verb.to(feat.device)
-        out = _NounsStage.apply(self, torch.is_grad_enabled(), feat, gt_verb, keep, seed, _mask_slot, self.role_emb.weight,
-                                self.verb_emb.weight, *self._ggnn_params(), self.nouns_classifier[1].weight,
-                                self.nouns_classifier[1].bias)
+        out, tap = _NounsStage.apply(self, torch.is_grad_enabled(), feat, gt_verb, keep, seed, _mask_slot,
+                                     self.role_emb.weight, self.verb_emb.weight, *self._ggnn_params(),
+                                     self.nouns_classifier[1].weight, self.nouns_classifier[1].bias)
         out._srg_stats = self._last_stats      # lets nouns_loss() reuse the classifier's per-tile softmax statistics
+        out._srg_tap = (tap, self._last_side) if (tap.requires_grad and self._last_side is not None) else None
         return out
 
     def predict_verb(self, img, batch_size, _feat=None):
@@ -591,9 +632,10 @@ class FCGGNN(nn.Module):
         if feat.shape[0] != batch_size:
             raise _lib.SrgError("batch_size %d does not match the features (%d)" % (batch_size, feat.shape[0]))
         keep, seed = self._dropout(0, feat.device)
-        out = _VerbStage.apply(self, torch.is_grad_enabled(), feat, keep, seed, 0, *self._ggnn_params(),
-                               self.verb_classifier[1].weight, self.verb_classifier[1].bias)
+        out, tap = _VerbStage.apply(self, torch.is_grad_enabled(), feat, keep, seed, 0, *self._ggnn_params(),
+                                    self.verb_classifier[1].weight, self.verb_classifier[1].bias)
         out._srg_stats = self._last_stats
+        out._srg_tap = (tap, self._last_side) if (tap.requires_grad and self._last_side is not None) else None
         return out
 
     def forward(self, img, gt_verb, img_nouns=None):
@@ -677,15 +719,25 @@ class FCGGNN(nn.Module):
             return None
         return st
 
+    @staticmethod
+    def _tap_of(logits, stats):
+        """(tap tensor, _GradTap) when `logits` is the very tensor a predict_* call returned in a differentiable
+        forward (same condition as for the softmax statistics), else (None, None)."""
+        tp = getattr(logits, "_srg_tap", None) if stats is not None else None
+        return tp if tp is not None else (None, None)
+
     def verb_loss(self, pred_verb, gt_verb):
         eng_pad = _pad256(self.encoder.get_num_verbs())
-        return _VerbLoss.apply(self, torch.is_grad_enabled(), pred_verb, gt_verb.to(pred_verb.device),
-                               self._stats_ptr(pred_verb, eng_pad) if pred_verb.dim() == 2 else None)
+        stats = self._stats_ptr(pred_verb, eng_pad) if pred_verb.dim() == 2 else None
+        tap, side = self._tap_of(pred_verb, stats)
+        return _VerbLoss.apply(self, torch.is_grad_enabled(), pred_verb, gt_verb.to(pred_verb.device), stats, tap, side)
 
     def nouns_loss(self, pred_nouns, gt_nouns):
         eng_pad = _pad256(self.encoder.get_num_labels())
-        return _NounsLoss.apply(self, torch.is_grad_enabled(), pred_nouns, gt_nouns.to(pred_nouns.device),
-                                self._stats_ptr(pred_nouns, eng_pad) if pred_nouns.dim() == 3 else None)
+        stats = self._stats_ptr(pred_nouns, eng_pad) if pred_nouns.dim() == 3 else None
+        tap, side = self._tap_of(pred_nouns, stats)
+        return _NounsLoss.apply(self, torch.is_grad_enabled(), pred_nouns, gt_nouns.to(pred_nouns.device), stats, tap,
+                                side)
 
     # ---- GGSNN.forward drop-in (inference) ------------------------------------------------------
     def _ggsnn_forward(self, hidden_state, mask=None, verb=False):

@@ -437,6 +437,37 @@ def test_argmax_agreement_with_real_margins(enc_syn):
     assert relmax(mpv, pv) <= BF16_TOL and relmax(mgpn, gpn) <= BF16_TOL
 
 
+def test_loss_gradient_routes_agree(enc_syn):
+    """d(loss)/d(logits) reaches the stage either through the side channel (the loss kernels write the bf16 operand of
+    the classifier's backward GEMMs straight into the stage's workspace; the `tap` output carries the autograd
+    dependency) or as an ordinary fp32 autograd gradient (any other consumer of the logits), or both at once."""
+    B, D = 16, 256
+    params = O.init_params(504, 190, 2001, D, seed=2)
+    fv, fn, gt_verb, gt_nouns = [x.cuda() for x in make_batch(enc_syn, B, D, seed=23)]
+
+    def run(route):
+        m = model_from(params, enc_syn, D, "bf16").eval()
+        pv, pn, _ = m(fv, gt_verb, img_nouns=fn)
+        assert pn._srg_tap is not None and pv._srg_tap is not None
+        if route == "tap":
+            loss = m.verb_loss(pv, gt_verb) + m.nouns_loss(pn, gt_nouns)
+        elif route == "autograd":          # a torch op in between: plain tensors, fp32 gradients through autograd
+            loss = m.verb_loss(pv * 1.0, gt_verb) + m.nouns_loss(pn * 1.0, gt_nouns)
+        else:                              # both routes into the same stage: the gradients add up
+            loss = m.verb_loss(pv, gt_verb) + m.nouns_loss(pn, gt_nouns) + \
+                0.5 * (m.verb_loss(pv * 1.0, gt_verb) + m.nouns_loss(pn * 1.0, gt_nouns)) + 0.25 * m.nouns_loss(pn, gt_nouns)
+        loss.backward()
+        return {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    tap, auto, both = run("tap"), run("autograd"), run("both")
+    for k in tap:
+        assert relmax(auto[k], tap[k]) <= 2e-3, (k, relmax(auto[k], tap[k]))
+        # verb: 1 + 0.5, nouns: 1 + 0.5 + 0.25 -- check the noun-only and verb-only tensors with their own factors
+    assert relmax(both["nouns_classifier.1.weight"], 1.75 * tap["nouns_classifier.1.weight"]) <= 1e-2
+    assert relmax(both["verb_classifier.1.weight"], 1.5 * tap["verb_classifier.1.weight"]) <= 1e-2
+    assert relmax(both["role_emb.weight"], 1.75 * tap["role_emb.weight"]) <= 1e-2
+
+
 def test_forward_features_equals_forward(enc_syn):
     """`forward_features` (the entry the cross-epoch feature cache uses) is `forward` minus the backbones."""
     m = S.FCGGNN(enc_syn, 256, backbone=None).cuda().eval()
