@@ -135,3 +135,23 @@ def test_two_rank_launcher(tmp_path):
     assert (w2 - w1).abs().max().item() <= 2 * 4 * 0.002 + 1e-4            # 4 steps of at most lr each, both ways
     assert torch.equal(two["model_state_dict"]["convnet_nouns.model.conv1.weight"],
                        one["model_state_dict"]["convnet_nouns.model.conv1.weight"])      # frozen, broadcast from rank 0
+
+
+@pytest.mark.gpu
+def test_e2e_eval_stream_tool(tmp_path):
+    """tools/bench_e2e_eval.py (BASELINE configs[4]) on a tiny stream: epoch 1 runs the backbones and fills the feature
+    cache, epoch 2 is served from it; the JSON line carries the per-epoch parts."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "bench_e2e_eval.py"), "--images", "48", "--batch",
+                          "32", "--epochs", "2", "--pool", "1", "--no-cpu-reference"], cwd=str(tmp_path),
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["metric"] == "e2e_eval_images_per_sec" and line["images"] == 48 and len(line["epochs"]) == 2
+    first, second = line["epochs"]
+    assert first["cache_misses"] == 48 and first["cache_hits"] == 0
+    assert second["cache_hits"] == 48 and second["cache_misses"] == 48            # cumulative counters
+    assert second["ms_backbones_or_cache"] < first["ms_backbones_or_cache"]
+    assert line["cached_epoch_images_per_sec"] > line["first_epoch_images_per_sec"]
